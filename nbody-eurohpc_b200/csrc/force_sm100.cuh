@@ -1,0 +1,349 @@
+// All-pairs softened-gravity force pass for sm_100a (B200).
+//
+// Replaces, from scratch, the reference's GPU force kernels
+//   src/murb/implem/SimulationNBodyCUDATileFullDevice.cu:53-153   (gpu+tile+full)
+//   src/murb/implem/SimulationNBodyCUDATileFullDevice200k.cu:102-175
+// and computes the same law as the oracle path
+//   src/murb/implem/SimulationNBodyNaive.cpp:34-53
+//     a_i = sum_j G m_j (q_j - q_i) / (|q_j - q_i|^2 + soft^2)^(3/2),  self term included (contributes 0).
+//
+// Design (B200-first, not a port):
+//  * Bodies live in HBM as AoSoA blocks of BLK=128 bodies: [x[128] | y[128] | z[128] | G*m[128]] = 2 KiB.
+//    One block is one contiguous TMA bulk copy (cp.async.bulk -> SASS UBLKCP) and, once in shared memory,
+//    is read as LDS.128 of four consecutive x / y / z / Gm values: exactly the operand shape of the
+//    Blackwell-only packed FP32 instructions (FFMA2/FADD2/FMUL2, PTX *.f32x2).
+//  * Two consecutive SOURCES (j, j+1) are processed per packed instruction against one target whose
+//    coordinates ptxas folds into the broadcast `.F32` operand form: 14 issue slots per 2 interactions
+//    (3 FADD2 + 6 FFMA2 + 3 FMUL2 + 2 MUFU.RSQ) instead of 26 scalar ones.
+//  * R targets are register-blocked per thread so one LDS.128 feeds 4*R interactions.
+//  * Source tiles are multi-buffered through shared memory by an mbarrier/TMA pipeline; the buffers are
+//    either shared by the CTA (one __syncthreads per tile) or private per warp (no CTA barrier at all).
+//  * The launch is a 2-D grid (target tiles x source chunks). Every CTA writes its partial sums to its
+//    own row of `partial`; the integrator kernel adds the rows in a fixed order, so results are
+//    deterministic and the grid can be sized to the 148 SMs independently of N.
+//  * Accuracy: per-tile accumulators (<= TJB*64 terms per packed half) are folded into a second-level
+//    accumulator after every tile, and chunk partials are summed in fp64 by the integrator, so the
+//    fp32 summation error does not grow with N (north-star bound: max |da|/|a| <= 1e-5 vs fp64).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200nb {
+
+constexpr int BLK = 128;                 // bodies per AoSoA block
+constexpr int BLK_FLOATS = 4 * BLK;      // x | y | z | gm
+constexpr int BLK_BYTES = BLK_FLOATS * 4;
+
+// float index of component `comp` (0=x,1=y,2=z,3=G*m) of body i inside a blocked array
+__host__ __device__ __forceinline__ size_t blk_index(size_t i, int comp)
+{
+    return (i / BLK) * (size_t)BLK_FLOATS + (size_t)comp * BLK + (i % BLK);
+}
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint64_t pk2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok;
+}
+// Bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------- launch args
+struct ForceArgs {
+    const float *src;            // blocked bodies the sources are read from (full replicated array)
+    const float *tgt;            // blocked bodies the targets are read from (same array on one GPU)
+    float *partial;              // [rows][3][tgt_stride] partial accelerations
+    uint32_t tgt_blk0;           // first target block inside `tgt`
+    uint32_t tgt_stride;         // floats per component row of `partial` (padded local target count)
+    uint32_t src_blk0, src_nblk; // source block range of this launch
+    uint32_t n_chunks;           // source chunks of this launch (== gridDim.y)
+    uint32_t row0;               // first partial row this launch writes
+    float soft2;
+    unsigned long long *dbg;     // optional: per-CTA {clock64 start,end, globaltimer start,end}
+};
+
+template <int THREADS, int R, int TJB, int ST, bool WARP_PRIVATE>
+constexpr size_t force_smem_bytes()
+{
+    return (size_t)(WARP_PRIVATE ? THREADS / 32 : 1) * ST * (TJB * BLK_BYTES + 8);
+}
+
+// ------------------------------------------------------------------------------------------- inner math
+// One AoSoA block (128 sources) against R register-blocked targets, packed f32x2 along the sources.
+template <int R, int U>
+__device__ __forceinline__ void block_packed(const float *__restrict__ sb, const float (&xi)[R], const float (&yi)[R],
+                                             const float (&zi)[R], uint64_t soft2p, uint64_t (&ax)[R],
+                                             uint64_t (&ay)[R], uint64_t (&az)[R])
+{
+#pragma unroll U
+    for (int j = 0; j < BLK; j += 4) {
+        const float4 xv = *reinterpret_cast<const float4 *>(sb + j);
+        const float4 yv = *reinterpret_cast<const float4 *>(sb + BLK + j);
+        const float4 zv = *reinterpret_cast<const float4 *>(sb + 2 * BLK + j);
+        const float4 gv = *reinterpret_cast<const float4 *>(sb + 3 * BLK + j);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t xj = h ? pk2(xv.z, xv.w) : pk2(xv.x, xv.y);
+            const uint64_t yj = h ? pk2(yv.z, yv.w) : pk2(yv.x, yv.y);
+            const uint64_t zj = h ? pk2(zv.z, zv.w) : pk2(zv.x, zv.y);
+            const uint64_t gj = h ? pk2(gv.z, gv.w) : pk2(gv.x, gv.y);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const uint64_t dx = sub2(xj, pk2(xi[k], xi[k]));
+                const uint64_t dy = sub2(yj, pk2(yi[k], yi[k]));
+                const uint64_t dz = sub2(zj, pk2(zi[k], zi[k]));
+                uint64_t d = fma2(dx, dx, soft2p);
+                d = fma2(dy, dy, d);
+                d = fma2(dz, dz, d);
+                float d0, d1;
+                upk2(d, d0, d1);
+                const uint64_t inv = pk2(rsqrt_approx(d0), rsqrt_approx(d1));
+                const uint64_t gi = mul2(gj, inv);
+                const uint64_t i2 = mul2(inv, inv);
+                const uint64_t f = mul2(i2, gi);
+                ax[k] = fma2(f, dx, ax[k]);
+                ay[k] = fma2(f, dy, ay[k]);
+                az[k] = fma2(f, dz, az[k]);
+            }
+        }
+    }
+}
+
+// Scalar FFMA/FMUL/FADD version of the same block (13 issue slots per interaction).
+template <int R, int U>
+__device__ __forceinline__ void block_scalar(const float *__restrict__ sb, const float (&xi)[R], const float (&yi)[R],
+                                             const float (&zi)[R], float soft2, float (&ax)[R], float (&ay)[R],
+                                             float (&az)[R])
+{
+#pragma unroll U
+    for (int j = 0; j < BLK; j += 4) {
+        const float4 xv = *reinterpret_cast<const float4 *>(sb + j);
+        const float4 yv = *reinterpret_cast<const float4 *>(sb + BLK + j);
+        const float4 zv = *reinterpret_cast<const float4 *>(sb + 2 * BLK + j);
+        const float4 gv = *reinterpret_cast<const float4 *>(sb + 3 * BLK + j);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+        const float zs[4] = {zv.x, zv.y, zv.z, zv.w};
+        const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const float dx = xs[q] - xi[k];
+                const float dy = ys[q] - yi[k];
+                const float dz = zs[q] - zi[k];
+                float d = fmaf(dx, dx, soft2);
+                d = fmaf(dy, dy, d);
+                d = fmaf(dz, dz, d);
+                const float inv = rsqrt_approx(d);
+                const float gi = gs[q] * inv;
+                const float i2 = inv * inv;
+                const float f = i2 * gi;
+                ax[k] = fmaf(f, dx, ax[k]);
+                ay[k] = fmaf(f, dy, ay[k]);
+                az[k] = fmaf(f, dz, az[k]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- the kernel
+// THREADS      threads per CTA (multiple of 32; THREADS*R must be a multiple of BLK)
+// R            targets per thread (register blocking)
+// TJB          AoSoA blocks (of 128 sources) per pipeline stage
+// ST           pipeline stages
+// PACKED       f32x2 instructions (true) or scalar FP32 (false)
+// WARP_PRIVATE each warp owns its stages and barriers (no CTA-wide barrier in the loop)
+// U            unroll of the 4-source inner step
+// MINB         min resident CTAs per SM for __launch_bounds__
+template <int THREADS, int R, int TJB, int ST, bool PACKED, bool WARP_PRIVATE, int U, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
+{
+    constexpr int TI = THREADS * R;
+    static_assert(TI % BLK == 0, "target tile must cover whole blocks");
+    constexpr int GROUPS = WARP_PRIVATE ? THREADS / 32 : 1;
+    constexpr int STAGE_FLOATS = TJB * BLK_FLOATS;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *stages = reinterpret_cast<float *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)GROUPS * ST * STAGE_FLOATS * 4);
+
+    const int grp = WARP_PRIVATE ? (int)(threadIdx.x >> 5) : 0;
+    const bool leader = WARP_PRIVATE ? ((threadIdx.x & 31) == 0) : (threadIdx.x == 0);
+    float *my_stages = stages + (size_t)grp * ST * STAGE_FLOATS;
+    const uint32_t my_stages_u32 = smem_u32(my_stages);
+    const uint32_t bar0 = smem_u32(bars + grp * ST);
+
+    unsigned long long t_clk0 = 0, t_ns0 = 0;
+    if (a.dbg != nullptr && threadIdx.x == 0) {
+        t_clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns0));
+    }
+
+    // balanced split of the source blocks over the chunks of this launch
+    const uint32_t c = blockIdx.y;
+    const uint32_t b_begin = a.src_blk0 + (uint32_t)(((uint64_t)a.src_nblk * c) / a.n_chunks);
+    const uint32_t b_end = a.src_blk0 + (uint32_t)(((uint64_t)a.src_nblk * (c + 1)) / a.n_chunks);
+    const uint32_t nblk = b_end - b_begin;
+    const uint32_t ntiles = (nblk + TJB - 1) / TJB;
+    const float *chunk_src = a.src + (size_t)b_begin * BLK_FLOATS;
+
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+    }
+    if (WARP_PRIVATE) __syncwarp(); else __syncthreads();
+
+    auto issue = [&](uint32_t tile, uint32_t stage) {
+        const uint32_t nb = min((uint32_t)TJB, nblk - tile * TJB);
+        const uint32_t bytes = nb * BLK_BYTES;
+        const uint32_t bar = bar0 + 8 * stage;
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(my_stages_u32 + stage * (STAGE_FLOATS * 4), chunk_src + (size_t)tile * STAGE_FLOATS, bytes, bar);
+    };
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s)
+            if ((uint32_t)s < ntiles) issue(s, s);
+    }
+
+    // register-blocked targets: thread owns local targets  blockIdx.x*TI + k*THREADS + threadIdx.x
+    float xi[R], yi[R], zi[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const size_t il = (size_t)blockIdx.x * TI + (size_t)k * THREADS + threadIdx.x;
+        const size_t ig = (size_t)a.tgt_blk0 * BLK + il;
+        xi[k] = __ldg(a.tgt + blk_index(ig, 0));
+        yi[k] = __ldg(a.tgt + blk_index(ig, 1));
+        zi[k] = __ldg(a.tgt + blk_index(ig, 2));
+    }
+
+    float mx[R], my[R], mz[R]; // second-level accumulators
+#pragma unroll
+    for (int k = 0; k < R; ++k) mx[k] = my[k] = mz[k] = 0.f;
+
+    const uint64_t soft2p = pk2(a.soft2, a.soft2);
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        const uint32_t s = t % ST;
+        const uint32_t parity = (t / ST) & 1u;
+        mbar_wait(bar0 + 8 * s, parity);
+        const float *sb = my_stages + (size_t)s * STAGE_FLOATS;
+        const uint32_t nb = min((uint32_t)TJB, nblk - t * TJB);
+
+        if (PACKED) {
+            uint64_t ax[R], ay[R], az[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) ax[k] = ay[k] = az[k] = 0ull;
+            for (uint32_t b = 0; b < nb; ++b) block_packed<R, U>(sb + b * BLK_FLOATS, xi, yi, zi, soft2p, ax, ay, az);
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                float lo, hi;
+                upk2(ax[k], lo, hi); mx[k] += lo + hi;
+                upk2(ay[k], lo, hi); my[k] += lo + hi;
+                upk2(az[k], lo, hi); mz[k] += lo + hi;
+            }
+        } else {
+            float ax[R], ay[R], az[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) ax[k] = ay[k] = az[k] = 0.f;
+            for (uint32_t b = 0; b < nb; ++b) block_scalar<R, U>(sb + b * BLK_FLOATS, xi, yi, zi, a.soft2, ax, ay, az);
+#pragma unroll
+            for (int k = 0; k < R; ++k) { mx[k] += ax[k]; my[k] += ay[k]; mz[k] += az[k]; }
+        }
+
+        if (t + ST < ntiles) { // refill the stage we just drained
+            if (WARP_PRIVATE) __syncwarp(); else __syncthreads();
+            if (leader) issue(t + ST, s);
+        }
+    }
+
+    const size_t row = (size_t)(a.row0 + c) * 3;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const size_t il = (size_t)blockIdx.x * TI + (size_t)k * THREADS + threadIdx.x;
+        a.partial[(row + 0) * a.tgt_stride + il] = mx[k];
+        a.partial[(row + 1) * a.tgt_stride + il] = my[k];
+        a.partial[(row + 2) * a.tgt_stride + il] = mz[k];
+    }
+
+    if (a.dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long t_ns1;
+        const unsigned long long t_clk1 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns1));
+        unsigned long long *d = a.dbg + 4ull * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+        d[0] = t_clk0; d[1] = t_clk1; d[2] = t_ns0; d[3] = t_ns1;
+    }
+}
+
+} // namespace b200nb

@@ -1,0 +1,380 @@
+// kbench: (1) FP32-pipe / packed-f32x2 / MUFU issue-rate microbenchmarks, (2) sweep of force_kernel variants.
+// Development tool, not part of the shipped library. Prints a table and writes JSON lines.
+//   kbench [--n N] [--reps K] [--micro 0|1] [--filter substr] [--out file] [--chunks S] [--check 0|1]
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../nbody-eurohpc_b200/csrc/force_sm100.cuh"
+#include "../nbody-eurohpc_b200/csrc/plan.hpp"
+
+using namespace b200nb;
+
+#define CK(x)                                                                                                          \
+    do {                                                                                                               \
+        cudaError_t e_ = (x);                                                                                          \
+        if (e_ != cudaSuccess) {                                                                                       \
+            fprintf(stderr, "CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__,                  \
+                    cudaGetErrorString(e_));                                                                           \
+            exit(2);                                                                                                   \
+        }                                                                                                              \
+    } while (0)
+
+// ----------------------------------------------------------------------------------------- microbenchmarks
+// Each thread runs ILP independent dependency chains; cycles are per-CTA clock64 deltas.
+template <int KIND, int ILP> // 0 FFMA, 1 FFMA2, 2 MUFU.RSQ, 3 FADD2 (broadcast operand), 4 FMUL2, 5 mix 12 f32x2 + 2 mufu
+__global__ void __launch_bounds__(256) ubench(float *out, unsigned long long *cyc, int iters, float seed)
+{
+    float v[ILP];
+    uint64_t p[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+        v[i] = seed + threadIdx.x * 1e-3f + i;
+        p[i] = pk2(v[i], v[i] + 0.5f);
+    }
+    const float c1 = seed * 0.999f, c2 = seed * 1e-3f;
+    const uint64_t pc1 = pk2(c1, c1), pc2 = pk2(c2, c2);
+    __syncthreads();
+    const unsigned long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                if (KIND == 0) v[i] = fmaf(v[i], c1, c2);
+                if (KIND == 1) p[i] = fma2(p[i], pc1, pc2);
+                if (KIND == 2) v[i] = rsqrt_approx(v[i]);
+                if (KIND == 3) p[i] = sub2(p[i], pk2(c2, c2));
+                if (KIND == 4) p[i] = mul2(p[i], pc1);
+                if (KIND == 5) { // same op mix as one packed interaction pair, fully dependent inside a chain
+                    uint64_t dx = sub2(p[i], pc2), dy = sub2(p[i], pc1), dz = sub2(pc1, p[i]);
+                    uint64_t d = fma2(dx, dx, pc2);
+                    d = fma2(dy, dy, d);
+                    d = fma2(dz, dz, d);
+                    float d0, d1;
+                    upk2(d, d0, d1);
+                    uint64_t inv = pk2(rsqrt_approx(d0), rsqrt_approx(d1));
+                    uint64_t gi = mul2(pc1, inv), i2 = mul2(inv, inv), f = mul2(i2, gi);
+                    p[i] = fma2(f, dx, p[i]);
+                    p[i] = fma2(f, dy, p[i]);
+                    p[i] = fma2(f, dz, p[i]);
+                }
+            }
+        }
+    }
+    const unsigned long long t1 = clock64();
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) {
+        float lo, hi;
+        upk2(p[i], lo, hi);
+        acc += v[i] + lo + hi;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int KIND, int ILP>
+static void run_ubench(const char *name, int ctas_per_sm, int sms, double instr_per_inner, FILE *jf)
+{
+    const int threads = 256, iters = 4096;
+    const int grid = sms * ctas_per_sm;
+    float *out;
+    unsigned long long *cyc;
+    CK(cudaMalloc(&out, (size_t)grid * threads * 4));
+    CK(cudaMalloc(&cyc, (size_t)grid * 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    ubench<KIND, ILP><<<grid, threads>>>(out, cyc, 64, 1.25f); // warm-up
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    ubench<KIND, ILP><<<grid, threads>>>(out, cyc, iters, 1.25f);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<unsigned long long> h(grid);
+    CK(cudaMemcpy(h.data(), cyc, (size_t)grid * 8, cudaMemcpyDeviceToHost));
+    unsigned long long mx = 0;
+    double avg = 0;
+    for (auto c : h) { mx = std::max(mx, c); avg += (double)c; }
+    avg /= grid;
+    // warp-instructions per SM = ctas_per_sm * 8 warps * iters * 8 * ILP * instr_per_inner
+    const double winstr_sm = (double)ctas_per_sm * (threads / 32) * iters * 8.0 * ILP * instr_per_inner;
+    const double ipc_sm = winstr_sm / (double)mx;
+    const double mhz = (double)mx / (ms * 1e3);
+    printf("  micro %-28s ilp=%d ctas/sm=%d : %6.3f warp-instr/clk/SM (max-cta cycles %llu, avg %.0f) ~%.0f MHz %.3f ms\n",
+           name, ILP, ctas_per_sm, ipc_sm, mx, avg, mhz, ms);
+    if (jf)
+        fprintf(jf, "{\"micro\":\"%s\",\"ilp\":%d,\"ctas_per_sm\":%d,\"warp_instr_per_clk_sm\":%.4f,\"mhz\":%.1f,\"ms\":%.4f}\n",
+                name, ILP, ctas_per_sm, ipc_sm, mhz, ms);
+    CK(cudaFree(out));
+    CK(cudaFree(cyc));
+    CK(cudaEventDestroy(e0));
+    CK(cudaEventDestroy(e1));
+}
+
+// ----------------------------------------------------------------------------------------- force variants
+struct Problem {
+    size_t n, n_pad;
+    float soft2;
+    float *d_bodies;                // blocked
+    float *d_partial;               // rows*3*n_pad
+    size_t partial_rows;
+    unsigned long long *d_dbg;
+    size_t dbg_ctas;
+    std::vector<float> hx, hy, hz, hg;
+    std::vector<size_t> check_idx;
+    std::vector<double> rx, ry, rz; // fp64 reference for check_idx
+    int sms;
+};
+
+struct Variant {
+    std::string name;
+    int threads, r, tjb, st, packed, warp_private, u, minb;
+    std::function<void(const ForceArgs &, dim3)> launch;
+    const void *fn;
+    size_t smem;
+};
+
+static std::vector<Variant> g_variants;
+
+template <int THREADS, int R, int TJB, int ST, bool PACKED, bool WP, int U, int MINB> static void reg_variant()
+{
+    Variant v;
+    char nm[128];
+    snprintf(nm, sizeof nm, "%s_t%d_r%d_tj%d_st%d_%s_u%d_mb%d", PACKED ? "pk" : "sc", THREADS, R, TJB, ST,
+             WP ? "warp" : "cta", U, MINB);
+    v.name = nm;
+    v.threads = THREADS; v.r = R; v.tjb = TJB; v.st = ST; v.packed = PACKED; v.warp_private = WP; v.u = U; v.minb = MINB;
+    auto k = force_kernel<THREADS, R, TJB, ST, PACKED, WP, U, MINB>;
+    v.fn = (const void *)k;
+    v.smem = force_smem_bytes<THREADS, R, TJB, ST, WP>();
+    v.launch = [k, smem = v.smem](const ForceArgs &a, dim3 grid) {
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, THREADS, smem>>>(a);
+    };
+    g_variants.push_back(v);
+}
+
+static void register_all()
+{
+    //            THR  R TJB ST PACK   WP    U MINB
+    reg_variant<256, 4, 2, 3, true, false, 2, 2>();
+    reg_variant<256, 4, 2, 3, true, false, 1, 2>();
+    reg_variant<256, 4, 2, 3, true, false, 4, 2>();
+    reg_variant<256, 2, 2, 3, true, false, 2, 3>();
+    reg_variant<256, 2, 2, 3, true, false, 2, 4>();
+    reg_variant<256, 1, 2, 3, true, false, 2, 4>();
+    reg_variant<256, 8, 2, 3, true, false, 1, 1>();
+    reg_variant<128, 4, 2, 3, true, false, 2, 4>();
+    reg_variant<128, 8, 2, 3, true, false, 1, 2>();
+    reg_variant<128, 8, 2, 3, true, false, 1, 3>();
+    reg_variant<256, 4, 4, 2, true, false, 2, 2>();
+    reg_variant<256, 4, 1, 4, true, false, 2, 2>();
+    reg_variant<256, 4, 1, 3, true, true, 2, 2>();
+    reg_variant<256, 2, 1, 3, true, true, 2, 3>();
+    reg_variant<128, 4, 1, 3, true, true, 2, 4>();
+    reg_variant<512, 2, 2, 3, true, false, 2, 1>();
+    reg_variant<512, 4, 2, 3, true, false, 2, 1>();
+    reg_variant<1024, 1, 2, 3, true, false, 2, 1>();
+    // scalar FP32 comparators (same pipeline, 13 issue slots / interaction)
+    reg_variant<256, 4, 2, 3, false, false, 1, 2>();
+    reg_variant<256, 4, 2, 3, false, false, 2, 2>();
+    reg_variant<256, 8, 2, 3, false, false, 1, 1>();
+    reg_variant<128, 8, 2, 3, false, false, 1, 2>();
+    reg_variant<256, 2, 2, 3, false, false, 2, 4>();
+    reg_variant<256, 4, 1, 3, false, true, 1, 2>();
+}
+
+static void make_problem(Problem &p, size_t n, int sms)
+{
+    p.n = n;
+    p.sms = sms;
+    const size_t align = 8192; // multiple of every THREADS*R used above
+    p.n_pad = (n + align - 1) / align * align;
+    p.soft2 = 2e8f * 2e8f;
+    p.hx.resize(p.n_pad); p.hy.resize(p.n_pad); p.hz.resize(p.n_pad); p.hg.resize(p.n_pad);
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        return (double)(s >> 11) / 9007199254740992.0;
+    };
+    const float G = 6.67384e-11f;
+    for (size_t i = 0; i < n; ++i) { // same box as the reference's "random" scheme (Bodies.cpp:217-257)
+        p.hg[i] = G * (float)(rnd() * 5e21);
+        p.hx[i] = (float)((rnd() * 2 - 1) * 5e8 * 1.33);
+        p.hy[i] = (float)((rnd() * 2 - 1) * 5e8);
+        p.hz[i] = (float)((rnd() * 2 - 1) * 5e8 - 10e8);
+    }
+    for (size_t i = n; i < p.n_pad; ++i) { p.hg[i] = 0.f; p.hx[i] = p.hx[n - 1]; p.hy[i] = p.hy[n - 1]; p.hz[i] = p.hz[n - 1]; }
+    std::vector<float> blocked(p.n_pad * 4);
+    for (size_t i = 0; i < p.n_pad; ++i) {
+        blocked[blk_index(i, 0)] = p.hx[i];
+        blocked[blk_index(i, 1)] = p.hy[i];
+        blocked[blk_index(i, 2)] = p.hz[i];
+        blocked[blk_index(i, 3)] = p.hg[i];
+    }
+    CK(cudaMalloc(&p.d_bodies, blocked.size() * 4));
+    CK(cudaMemcpy(p.d_bodies, blocked.data(), blocked.size() * 4, cudaMemcpyHostToDevice));
+    p.partial_rows = 64;
+    CK(cudaMalloc(&p.d_partial, p.partial_rows * 3 * p.n_pad * 4));
+    p.dbg_ctas = 1 << 20;
+    CK(cudaMalloc(&p.d_dbg, p.dbg_ctas * 32));
+    // fp64 reference on a handful of targets
+    const int ncheck = 96;
+    for (int c = 0; c < ncheck; ++c) p.check_idx.push_back((size_t)((double)c / ncheck * n) + (c % 7));
+    p.check_idx.back() = n - 1;
+    p.rx.assign(ncheck, 0); p.ry.assign(ncheck, 0); p.rz.assign(ncheck, 0);
+    for (int c = 0; c < ncheck; ++c) {
+        const size_t i = std::min(p.check_idx[c], n - 1);
+        p.check_idx[c] = i;
+        double ax = 0, ay = 0, az = 0;
+        for (size_t j = 0; j < n; ++j) {
+            const double dx = (double)p.hx[j] - p.hx[i], dy = (double)p.hy[j] - p.hy[i], dz = (double)p.hz[j] - p.hz[i];
+            const double d = dx * dx + dy * dy + dz * dz + (double)p.soft2;
+            const double f = (double)p.hg[j] / (d * std::sqrt(d));
+            ax += f * dx; ay += f * dy; az += f * dz;
+        }
+        p.rx[c] = ax; p.ry[c] = ay; p.rz[c] = az;
+    }
+}
+
+int main(int argc, char **argv)
+{
+    size_t n = 200000;
+    int reps = 3, micro = 1, chunks_override = 0, check = 1;
+    std::string filter, outpath = "gpurun_out/kbench.jsonl";
+    for (int i = 1; i < argc; ++i) {
+        auto arg = [&](const char *k) { return !strcmp(argv[i], k) && i + 1 < argc; };
+        if (arg("--n")) n = strtoull(argv[++i], 0, 10);
+        else if (arg("--reps")) reps = atoi(argv[++i]);
+        else if (arg("--micro")) micro = atoi(argv[++i]);
+        else if (arg("--filter")) filter = argv[++i];
+        else if (arg("--out")) outpath = argv[++i];
+        else if (arg("--chunks")) chunks_override = atoi(argv[++i]);
+        else if (arg("--check")) check = atoi(argv[++i]);
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    printf("device: %s, %d SMs, cc %d.%d, clockRate %d kHz\n", prop.name, sms, prop.major, prop.minor, prop.clockRate);
+    FILE *jf = fopen(outpath.c_str(), "a");
+
+    if (micro) {
+        printf("== pipe microbenchmarks (256 thr/CTA; warp-instructions per clock per SM; 4.0 = one per SMSP per clock)\n");
+        run_ubench<0, 8>("FFMA", 4, sms, 1, jf);
+        run_ubench<0, 8>("FFMA", 8, sms, 1, jf);
+        run_ubench<1, 8>("FFMA2 (fma.rn.f32x2)", 4, sms, 1, jf);
+        run_ubench<1, 8>("FFMA2 (fma.rn.f32x2)", 8, sms, 1, jf);
+        run_ubench<1, 4>("FFMA2 (fma.rn.f32x2)", 8, sms, 1, jf);
+        run_ubench<3, 8>("FADD2 bcast", 4, sms, 1, jf);
+        run_ubench<4, 8>("FMUL2", 4, sms, 1, jf);
+        run_ubench<2, 8>("MUFU.RSQ", 4, sms, 1, jf);
+        run_ubench<5, 4>("mix 12xf32x2+2xMUFU", 4, sms, 14, jf);
+        run_ubench<5, 4>("mix 12xf32x2+2xMUFU", 2, sms, 14, jf);
+        run_ubench<5, 2>("mix 12xf32x2+2xMUFU", 4, sms, 14, jf);
+    }
+
+    register_all();
+    Problem p;
+    make_problem(p, n, sms);
+    printf("== force variants, N=%zu (padded %zu), soft=2e8; int/clk/SM uses in-kernel clock64/globaltimer MHz\n", n, p.n_pad);
+    printf("%-34s %4s %5s %3s %6s %6s %9s %9s %8s %8s %9s\n", "variant", "regs", "smemK", "occ", "chunks", "waves",
+           "ms", "Gint/s", "MHz", "i/clk/SM", "maxrelerr");
+
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (auto &v : g_variants) {
+        if (!filter.empty() && v.name.find(filter) == std::string::npos) continue;
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, v.fn));
+        CK(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem));
+        if (occ < 1) { printf("%-34s cannot launch (occ 0)\n", v.name.c_str()); continue; }
+        const uint32_t ti = v.threads * v.r;
+        const uint32_t n_itiles = (uint32_t)(p.n_pad / ti);
+        const uint32_t n_blocks = (uint32_t)(p.n_pad / BLK);
+        ChunkPlan plan = plan_chunks(n_itiles, n_blocks, (uint32_t)(sms * occ), (uint32_t)(2 * v.tjb), (uint32_t)p.partial_rows);
+        if (chunks_override > 0) plan.n_chunks = chunks_override;
+        ForceArgs a{};
+        a.src = p.d_bodies; a.tgt = p.d_bodies; a.partial = p.d_partial;
+        a.tgt_blk0 = 0; a.tgt_stride = (uint32_t)p.n_pad;
+        a.src_blk0 = 0; a.src_nblk = n_blocks; a.n_chunks = plan.n_chunks; a.row0 = 0;
+        a.soft2 = p.soft2;
+        dim3 grid(n_itiles, plan.n_chunks);
+        const size_t ctas = (size_t)n_itiles * plan.n_chunks;
+        a.dbg = ctas <= p.dbg_ctas ? p.d_dbg : nullptr;
+        v.launch(a, grid); // warm-up
+        CK(cudaGetLastError());
+        cudaError_t se = cudaDeviceSynchronize();
+        if (se != cudaSuccess) {
+            printf("%-34s FAILED: %s\n", v.name.c_str(), cudaGetErrorString(se));
+            if (jf) { fprintf(jf, "{\"variant\":\"%s\",\"error\":\"%s\"}\n", v.name.c_str(), cudaGetErrorString(se)); fclose(jf); }
+            return 3; // context is dead after a trap
+        }
+        float best_ms = 1e30f;
+        for (int r = 0; r < reps; ++r) {
+            CK(cudaEventRecord(e0));
+            v.launch(a, grid);
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            best_ms = std::min(best_ms, ms);
+        }
+        // SM clock from the last run: sum of CTA cycle spans / sum of CTA ns spans
+        double mhz = 0;
+        if (a.dbg) {
+            std::vector<unsigned long long> h(ctas * 4);
+            CK(cudaMemcpy(h.data(), p.d_dbg, ctas * 32, cudaMemcpyDeviceToHost));
+            double cyc = 0, ns = 0;
+            for (size_t c = 0; c < ctas; ++c) { cyc += (double)(h[4 * c + 1] - h[4 * c]); ns += (double)(h[4 * c + 3] - h[4 * c + 2]); }
+            mhz = cyc / ns * 1e3;
+        }
+        // accuracy: sum partial rows on the host in fp64 for the checked targets
+        double maxrel = -1;
+        if (check) {
+            std::vector<float> hp((size_t)plan.n_chunks * 3 * p.n_pad);
+            CK(cudaMemcpy(hp.data(), p.d_partial, hp.size() * 4, cudaMemcpyDeviceToHost));
+            maxrel = 0;
+            for (size_t c = 0; c < p.check_idx.size(); ++c) {
+                const size_t i = p.check_idx[c];
+                double ax = 0, ay = 0, az = 0;
+                for (uint32_t s = 0; s < plan.n_chunks; ++s) {
+                    ax += hp[((size_t)s * 3 + 0) * p.n_pad + i];
+                    ay += hp[((size_t)s * 3 + 1) * p.n_pad + i];
+                    az += hp[((size_t)s * 3 + 2) * p.n_pad + i];
+                }
+                const double dxe = ax - p.rx[c], dye = ay - p.ry[c], dze = az - p.rz[c];
+                const double num = std::sqrt(dxe * dxe + dye * dye + dze * dze);
+                const double den = std::sqrt(p.rx[c] * p.rx[c] + p.ry[c] * p.ry[c] + p.rz[c] * p.rz[c]);
+                maxrel = std::max(maxrel, num / den);
+            }
+        }
+        const double inter = (double)p.n_pad * (double)p.n_pad; // padded pairs are computed too
+        const double gints = inter / (best_ms * 1e-3) / 1e9;
+        const double useful = (double)n * (double)n / (best_ms * 1e-3) / 1e9;
+        const double ipc = mhz > 0 ? inter / (best_ms * 1e-3) / (mhz * 1e6) / sms : 0;
+        printf("%-34s %4d %5.1f %3d %6u %6u %9.3f %9.1f %8.0f %8.3f %9.2e\n", v.name.c_str(), fa.numRegs, v.smem / 1024.0,
+               occ, plan.n_chunks, plan.waves, best_ms, useful, mhz, ipc, maxrel);
+        if (jf) {
+            fprintf(jf,
+                    "{\"variant\":\"%s\",\"n\":%zu,\"regs\":%d,\"smem\":%zu,\"occ\":%d,\"chunks\":%u,\"waves\":%u,\"ms\":%.4f,"
+                    "\"gints_useful\":%.2f,\"gints_padded\":%.2f,\"mhz\":%.1f,\"int_per_clk_sm\":%.4f,\"maxrelerr\":%.3e}\n",
+                    v.name.c_str(), n, fa.numRegs, v.smem, occ, plan.n_chunks, plan.waves, best_ms, useful, gints, mhz, ipc,
+                    maxrel);
+            fflush(jf);
+        }
+    }
+    if (jf) fclose(jf);
+    return 0;
+}
