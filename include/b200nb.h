@@ -105,6 +105,9 @@ int b200nb_energy(b200nb_ctx *ctx, double *total);
 int b200nb_sync(b200nb_ctx *ctx);
 
 /* ---- introspection / measurement ------------------------------------------------------------------------------ */
+/* Targets per rank L (host only): rank r owns global bodies [r*L, min((r+1)*L, n)).  Contiguous, balanced to the
+ * 1024-body launch granularity; the analogue of buildCountsDispls (SimulationNBodyMultiNode.cpp:76-91). */
+uint64_t b200nb_slice_length(uint64_t n_bodies, int n_ranks);
 uint64_t b200nb_n_bodies(const b200nb_ctx *ctx);
 int b200nb_n_local_gpus(const b200nb_ctx *ctx);
 uint64_t b200nb_allocated_bytes(const b200nb_ctx *ctx); /* device bytes, all local GPUs */
@@ -120,6 +123,10 @@ int b200nb_event_elapsed_ms(b200nb_ctx *ctx, int slot_start, int slot_stop, floa
  * force kernels and their launch count since the last enable (joins the devices). */
 int b200nb_profile_enable(b200nb_ctx *ctx, int on);
 int b200nb_profile_get(b200nb_ctx *ctx, double *force_ms_total, uint64_t *force_launches);
+
+/* Evicts the L2 between timed steps: overwrites a 256 MiB scratch buffer (larger than the 126 MB L2) on the compute
+ * stream(s) with cudaMemsetAsync.  Measurement hygiene only; the hot path never calls it. */
+int b200nb_flush_l2(b200nb_ctx *ctx);
 
 /* Page-locked host buffers for the end-to-end path (cudaHostAlloc / cudaFreeHost). */
 int b200nb_host_alloc(void **ptr, uint64_t bytes);

@@ -1,0 +1,753 @@
+// libb200nb: context, sharding, streams/events, NCCL exchange and the C ABI declared in include/b200nb.h.
+//
+// One context drives one or more "shards" (one per GPU).  A shard owns a contiguous range of L targets and keeps
+//   bodies  : the FULL system as AoSoA blocks (positions + G*m), 16 B/body, replicated on every GPU
+//   vel/acc : SoA [3][L] for its own targets,  mass [L],  partial [S][3][L] chunk partial sums
+// State replication + target sharding is the reference's only distributed strategy
+// (src/murb/implem/SimulationNBodyMultiNode.cpp:76-148: MPI_Allgatherv of qx,qy,qz,m then of ax,ay,az); here the
+// exchange is ONE in-place ncclAllGather of the blocked slice per step on a communication stream, overlapped with
+// the force pass over the rank's own (already resident) source chunks, and no acceleration gather at all because
+// every GPU integrates only its own targets.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200nb.h"
+#include "integrate_sm100.cuh"
+#include "plan.hpp"
+
+using namespace b200nb;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ NCCL (lazy)
+// Loaded with dlopen only when more than one rank is requested, so single-GPU use has no NCCL dependency.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load()
+    {
+        if (handle) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+#define LOADSYM(field, sym)                                                                                            \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, sym));                                                     \
+    if (!field) { err = std::string("missing NCCL symbol ") + sym; return false; }
+        LOADSYM(GetUniqueId, "ncclGetUniqueId");
+        LOADSYM(CommInitRank, "ncclCommInitRank");
+        LOADSYM(CommDestroy, "ncclCommDestroy");
+        LOADSYM(GroupStart, "ncclGroupStart");
+        LOADSYM(GroupEnd, "ncclGroupEnd");
+        LOADSYM(AllGather, "ncclAllGather");
+        LOADSYM(AllReduce, "ncclAllReduce");
+        LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------ kernel table
+typedef void (*ForceKernelFn)(const ForceArgs);
+struct KernelVariant {
+    const char *name;
+    ForceKernelFn fn;
+    int threads, r, tjb, st;
+    size_t smem;
+};
+#define VARIANT(NAME, THREADS, R, TJB, ST, PACKED, WP, U, MINB)                                                        \
+    KernelVariant { NAME, force_kernel<THREADS, R, TJB, ST, PACKED, WP, U, MINB>, THREADS, R, TJB, ST,                 \
+                    force_smem_bytes<THREADS, R, TJB, ST, WP>() }
+const KernelVariant g_variants[] = {
+    // default first; chosen from the B200 sweep in profiles/ (tools/kbench)
+    VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, true, false, 2, 3),
+    VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, true, false, 1, 2),
+    VARIANT("pk_t256_r4_tj4_st2_cta_u2_mb2", 256, 4, 4, 2, true, false, 2, 2),
+    VARIANT("sc_t256_r4_tj2_st3_cta_u1_mb2", 256, 4, 2, 3, false, false, 1, 2),
+};
+constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
+constexpr uint64_t SLICE_ALIGN = 1024; // multiple of THREADS*R of every variant and of BLK
+constexpr uint32_t MAX_ROWS = 64;
+constexpr int N_TIMER_SLOTS = 8;
+
+struct Shard {
+    int rank = 0, device = 0;
+    cudaStream_t s_compute = nullptr, s_comm = nullptr;
+    cudaEvent_t ev_integrated = nullptr, ev_gathered = nullptr;
+    cudaEvent_t timer[N_TIMER_SLOTS] = {};
+    float *bodies = nullptr, *vel = nullptr, *acc = nullptr, *mass = nullptr, *partial = nullptr, *stage = nullptr;
+    double *energy_blocks = nullptr, *energy_out = nullptr;
+    void *l2_scratch = nullptr;
+    ncclComm_t comm = nullptr;
+    int n_sms = 0, occ = 0;
+    uint32_t n_local = 0; // real bodies in the slice
+    std::vector<cudaEvent_t> prof; // pairs (start, stop) around force launches
+    uint64_t bytes = 0;
+};
+
+} // namespace
+
+struct b200nb_ctx {
+    uint64_t n = 0;
+    int n_ranks = 1;
+    uint64_t L = 0, total_pad = 0, stage_stride = 0;
+    uint32_t nblk_total = 0;
+    float G = 0.f, soft = 0.f, soft2 = 0.f;
+    const KernelVariant *kv = nullptr;
+    uint32_t k_per_slice = 1, rows = 1; // S = k_per_slice * n_ranks
+    std::vector<Shard> shards;
+    bool uploaded = false, acc_valid = false, profiling = false;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) saved = -1; }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
+int fail(b200nb_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(c, call)                                                                                                    \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            return fail(c, B200NB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+    } while (0)
+#define NC(c, call)                                                                                                    \
+    do {                                                                                                               \
+        ncclResult_t r_ = (call);                                                                                      \
+        if (r_ != ncclSuccess)                                                                                         \
+            return fail(c, B200NB_ENCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+// chunks per slice k (S = k*P): maximise CTAs / (waves * slots) over the two launches of a step
+// (own-slice chunks [0,k) and remote chunks [k,S)); for P == 1 it is the single-launch plan.
+uint32_t plan_k(uint32_t n_itiles, uint32_t blocks_per_slice, uint32_t slots, int tjb, int n_ranks)
+{
+    if (n_ranks == 1) return plan_chunks(n_itiles, blocks_per_slice, slots, 2u * tjb, MAX_ROWS).n_chunks;
+    const uint32_t k_hi = std::max(1u, std::min(MAX_ROWS / (uint32_t)n_ranks, blocks_per_slice / (2u * tjb)));
+    uint32_t best = 1;
+    double best_score = -1;
+    for (uint32_t k = 1; k <= k_hi; ++k) {
+        const uint64_t ma = (uint64_t)n_itiles * k, mb = ma * (n_ranks - 1);
+        const uint64_t wa = (ma + slots - 1) / slots, wb = (mb + slots - 1) / slots;
+        const double eff = (double)(ma + mb) / (double)((wa + wb) * slots);
+        const double ragged = (double)blocks_per_slice / (double)(k * ((blocks_per_slice + k - 1) / k));
+        const double score = eff * ragged - 1e-4 * k;
+        if (score > best_score) { best_score = score; best = k; }
+    }
+    return best;
+}
+
+int alloc_shard(b200nb_ctx *c, Shard &s)
+{
+    CU(c, cudaSetDevice(s.device));
+    cudaDeviceProp prop;
+    CU(c, cudaGetDeviceProperties(&prop, s.device));
+    if (prop.major < 10)
+        return fail(c, B200NB_ECUDA, "device %d is sm_%d%d; libb200nb is built for sm_100a only", s.device, prop.major,
+                    prop.minor);
+    s.n_sms = prop.multiProcessorCount;
+    CU(c, cudaStreamCreateWithFlags(&s.s_compute, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
+    CU(c, cudaEventCreateWithFlags(&s.ev_integrated, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&s.ev_gathered, cudaEventDisableTiming));
+    for (auto &t : s.timer) CU(c, cudaEventCreate(&t));
+    CU(c, cudaFuncSetAttribute(c->kv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kv->smem));
+    CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ, c->kv->fn, c->kv->threads, c->kv->smem));
+    if (s.occ < 1) return fail(c, B200NB_ECUDA, "force kernel %s cannot be resident on device %d", c->kv->name, s.device);
+    const uint64_t first = (uint64_t)s.rank * c->L;
+    s.n_local = first >= c->n ? 0u : (uint32_t)std::min<uint64_t>(c->L, c->n - first);
+    return B200NB_OK;
+}
+
+int alloc_buffers(b200nb_ctx *c, Shard &s)
+{
+    CU(c, cudaSetDevice(s.device));
+    const size_t L = c->L;
+    auto dmalloc = [&](void **p, size_t bytes) -> cudaError_t { s.bytes += bytes; return cudaMalloc(p, bytes); };
+    CU(c, dmalloc((void **)&s.bodies, c->total_pad * 16));
+    CU(c, dmalloc((void **)&s.vel, 3 * L * 4));
+    CU(c, dmalloc((void **)&s.acc, 3 * L * 4));
+    CU(c, dmalloc((void **)&s.mass, L * 4));
+    CU(c, dmalloc((void **)&s.partial, (size_t)c->rows * 3 * L * 4));
+    CU(c, dmalloc((void **)&s.stage, 7 * c->stage_stride * 4));
+    const size_t eb = (L + ENERGY_THREADS - 1) / ENERGY_THREADS;
+    CU(c, dmalloc((void **)&s.energy_blocks, eb * 8));
+    CU(c, dmalloc((void **)&s.energy_out, 8));
+    CU(c, cudaMemsetAsync(s.acc, 0, 3 * L * 4, s.s_compute));
+    CU(c, cudaMemsetAsync(s.vel, 0, 3 * L * 4, s.s_compute));
+    CU(c, cudaEventRecord(s.ev_gathered, s.s_comm)); // "positions are current" before the first step
+    return B200NB_OK;
+}
+
+const KernelVariant *pick_variant()
+{
+    const char *e = getenv("B200NB_VARIANT");
+    if (e && *e) {
+        for (int i = 0; i < N_VARIANTS; ++i)
+            if (!strcmp(e, g_variants[i].name)) return &g_variants[i];
+        const long idx = strtol(e, nullptr, 10);
+        if (idx >= 0 && idx < N_VARIANTS && e[0] >= '0' && e[0] <= '9') return &g_variants[idx];
+        fprintf(stderr, "libb200nb: unknown B200NB_VARIANT '%s', using %s\n", e, g_variants[0].name);
+    }
+    return &g_variants[0];
+}
+
+int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks, const std::vector<int> &ranks,
+                  const std::vector<int> &devices, const void *nccl_id)
+{
+    if (!out) return fail(nullptr, B200NB_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n == 0 || n > (1ull << 31)) return fail(nullptr, B200NB_EINVAL, "n_bodies must be in [1, 2^31]");
+    if (!(soft != 0.f)) return fail(nullptr, B200NB_EINVAL, "softening factor can't be equal to 0 (main.cpp:150-155)");
+    DeviceGuard guard;
+    b200nb_ctx *c = new b200nb_ctx();
+    c->n = n; c->n_ranks = n_ranks; c->G = G; c->soft = soft; c->soft2 = soft * soft;
+    c->kv = pick_variant();
+    c->L = b200nb_slice_length(n, n_ranks);
+    c->total_pad = c->L * n_ranks;
+    c->nblk_total = (uint32_t)(c->total_pad / BLK);
+    c->stage_stride = (n + 3) / 4 * 4;
+    c->shards.resize(ranks.size());
+    auto bail = [&](int code) {
+        g_create_error = c->err;
+        b200nb_destroy(c);
+        return code;
+    };
+    for (size_t i = 0; i < ranks.size(); ++i) {
+        c->shards[i].rank = ranks[i];
+        c->shards[i].device = devices[i];
+        if (int rc = alloc_shard(c, c->shards[i])) return bail(rc);
+    }
+    const Shard &s0 = c->shards[0];
+    const uint32_t ti = c->kv->threads * c->kv->r;
+    c->k_per_slice = plan_k((uint32_t)(c->L / ti), (uint32_t)(c->L / BLK), (uint32_t)(s0.n_sms * s0.occ), c->kv->tjb, n_ranks);
+    c->rows = c->k_per_slice * n_ranks;
+    for (auto &s : c->shards)
+        if (int rc = alloc_buffers(c, s)) return bail(rc);
+
+    if (n_ranks > 1) {
+        if (!g_nccl.load()) { c->err = g_nccl.err; return bail(B200NB_ENCCL); }
+        ncclUniqueId id;
+        if (nccl_id) memcpy(&id, nccl_id, sizeof id);
+        else if (ranks.size() == (size_t)n_ranks) {
+            ncclResult_t r = g_nccl.GetUniqueId(&id);
+            if (r != ncclSuccess) { c->err = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return bail(B200NB_ENCCL); }
+        } else { c->err = "nccl_id is required when this process does not own every rank"; return bail(B200NB_EINVAL); }
+        ncclResult_t r = g_nccl.GroupStart();
+        for (auto &s : c->shards) {
+            if (r != ncclSuccess) break;
+            if (cudaSetDevice(s.device) != cudaSuccess) { r = ncclUnhandledCudaError; break; }
+            r = g_nccl.CommInitRank(&s.comm, n_ranks, id, s.rank);
+        }
+        ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = r2;
+        if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return bail(B200NB_ENCCL); }
+    }
+    *out = c;
+    return B200NB_OK;
+}
+
+// enqueue the force pass (own chunks, wait for the gather, remote chunks) on every shard's compute stream
+int enqueue_force(b200nb_ctx *c)
+{
+    const KernelVariant &kv = *c->kv;
+    const uint32_t ti = kv.threads * kv.r;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        ForceArgs a{};
+        a.src = s.bodies; a.tgt = s.bodies; a.partial = s.partial;
+        a.tgt_blk0 = (uint32_t)((uint64_t)s.rank * c->L / BLK);
+        a.tgt_stride = (uint32_t)c->L;
+        a.src_nblk_total = c->nblk_total;
+        a.n_chunks_total = c->rows;
+        a.chunk_rot = c->k_per_slice * (uint32_t)s.rank;
+        a.soft2 = c->soft2;
+        a.dbg = nullptr;
+        const uint32_t n_itiles = (uint32_t)(c->L / ti);
+        auto launch = [&](uint32_t first, uint32_t count) -> cudaError_t {
+            a.chunk_first = first;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (c->profiling) {
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaEventRecord(e0, s.s_compute);
+            }
+            kv.fn<<<dim3(n_itiles, count), kv.threads, kv.smem, s.s_compute>>>(a);
+            if (c->profiling) { cudaEventRecord(e1, s.s_compute); s.prof.push_back(e0); s.prof.push_back(e1); }
+            c->launches++;
+            return cudaGetLastError();
+        };
+        if (c->n_ranks == 1) {
+            CU(c, launch(0, c->rows));
+        } else {
+            CU(c, launch(0, c->k_per_slice));                          // own slice: resident, overlaps the all-gather
+            CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0)); // remote slices must have landed
+            CU(c, launch(c->k_per_slice, c->rows - c->k_per_slice));
+        }
+    }
+    return B200NB_OK;
+}
+
+int enqueue_integrate(b200nb_ctx *c, int mode, float dt)
+{
+    for (auto &s : c->shards) {
+        if (s.n_local == 0) continue;
+        CU(c, cudaSetDevice(s.device));
+        IntegrateArgs a{};
+        a.bodies = s.bodies; a.vel = s.vel; a.acc = s.acc; a.partial = s.partial;
+        a.rows = c->rows; a.L = (uint32_t)c->L; a.n_local = s.n_local;
+        a.first = (uint64_t)s.rank * c->L; a.dt = dt; a.mode = mode;
+        integrate_kernel<<<(s.n_local + 255) / 256, 256, 0, s.s_compute>>>(a);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    return B200NB_OK;
+}
+
+// positions of the own slice changed: publish them to every other rank (in place, on the comm stream)
+int enqueue_gather(b200nb_ctx *c)
+{
+    if (c->n_ranks == 1) return B200NB_OK;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        CU(c, cudaEventRecord(s.ev_integrated, s.s_compute));
+        CU(c, cudaStreamWaitEvent(s.s_comm, s.ev_integrated, 0));
+    }
+    NC(c, g_nccl.GroupStart());
+    ncclResult_t r = ncclSuccess;
+    for (auto &s : c->shards) {
+        if (cudaSetDevice(s.device) != cudaSuccess) { r = ncclUnhandledCudaError; break; }
+        const size_t count = (size_t)c->L * 4; // floats in one blocked slice
+        r = g_nccl.AllGather(s.bodies + (size_t)s.rank * count, s.bodies, count, ncclFloat, s.comm, s.s_comm);
+        if (r != ncclSuccess) break;
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) return fail(c, B200NB_ENCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r));
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        CU(c, cudaEventRecord(s.ev_gathered, s.s_comm));
+    }
+    return B200NB_OK;
+}
+
+int sync_all(b200nb_ctx *c)
+{
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        CU(c, cudaStreamSynchronize(s.s_compute));
+        CU(c, cudaStreamSynchronize(s.s_comm));
+    }
+    return B200NB_OK;
+}
+
+// gather a [3][L] per-rank device array (vel or acc) into host SoA arrays of n floats
+int download_sliced(b200nb_ctx *c, float *Shard::*field, float *hx, float *hy, float *hz)
+{
+    float *dst[3] = {hx, hy, hz};
+    const bool all_local = c->shards.size() == (size_t)c->n_ranks;
+    if (all_local) {
+        for (auto &s : c->shards) {
+            if (s.n_local == 0) continue;
+            CU(c, cudaSetDevice(s.device));
+            for (int k = 0; k < 3; ++k)
+                if (dst[k])
+                    CU(c, cudaMemcpyAsync(dst[k] + (size_t)s.rank * c->L, (s.*field) + (size_t)k * c->L,
+                                          (size_t)s.n_local * 4, cudaMemcpyDeviceToHost, s.s_compute));
+        }
+        return sync_all(c);
+    }
+    // one rank per process: all-gather the slices through a temporary [P][3][L] device buffer
+    Shard &s = c->shards[0];
+    CU(c, cudaSetDevice(s.device));
+    float *tmp = nullptr;
+    const size_t count = 3 * (size_t)c->L;
+    CU(c, cudaMalloc((void **)&tmp, count * c->n_ranks * 4));
+    CU(c, cudaMemcpyAsync(tmp + (size_t)s.rank * count, s.*field, count * 4, cudaMemcpyDeviceToDevice, s.s_compute));
+    ncclResult_t r = g_nccl.AllGather(tmp + (size_t)s.rank * count, tmp, count, ncclFloat, s.comm, s.s_compute);
+    if (r != ncclSuccess) { cudaFree(tmp); return fail(c, B200NB_ENCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r)); }
+    for (int rk = 0; rk < c->n_ranks; ++rk) {
+        const uint64_t first = (uint64_t)rk * c->L;
+        if (first >= c->n) break;
+        const size_t cnt = (size_t)std::min<uint64_t>(c->L, c->n - first);
+        for (int k = 0; k < 3; ++k)
+            if (dst[k])
+                CU(c, cudaMemcpyAsync(dst[k] + first, tmp + (size_t)rk * count + (size_t)k * c->L, cnt * 4,
+                                      cudaMemcpyDeviceToHost, s.s_compute));
+    }
+    CU(c, cudaStreamSynchronize(s.s_compute));
+    CU(c, cudaFree(tmp));
+    return B200NB_OK;
+}
+
+} // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+int b200nb_create(b200nb_ctx **out, uint64_t n_bodies, int n_gpus, float G, float soft)
+{
+    int cur = 0, visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1)
+        return fail(nullptr, B200NB_ECUDA, "no CUDA device visible (libb200nb has no CPU fallback)");
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    if (n_gpus < 0 || n_gpus > visible) return fail(nullptr, B200NB_EINVAL, "n_gpus=%d but %d device(s) visible", n_gpus, visible);
+    if (n_gpus == 0) n_gpus = visible;
+    std::vector<int> ranks, devices;
+    for (int i = 0; i < n_gpus; ++i) {
+        ranks.push_back(i);
+        devices.push_back(n_gpus == 1 ? cur : i);
+    }
+    return create_common(out, n_bodies, G, soft, n_gpus, ranks, devices, nullptr);
+}
+
+int b200nb_create_rank(b200nb_ctx **out, uint64_t n_bodies, float G, float soft, int rank, int n_ranks, int device,
+                       const void *nccl_id)
+{
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(nullptr, B200NB_EINVAL, "bad rank %d of %d", rank, n_ranks);
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1)
+        return fail(nullptr, B200NB_ECUDA, "no CUDA device visible (libb200nb has no CPU fallback)");
+    if (device < 0 || device >= visible) return fail(nullptr, B200NB_EINVAL, "device %d not visible", device);
+    if (n_ranks > 1 && !nccl_id) return fail(nullptr, B200NB_EINVAL, "nccl_id is required for n_ranks > 1");
+    return create_common(out, n_bodies, G, soft, n_ranks, {rank}, {device}, nccl_id);
+}
+
+int b200nb_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(nullptr, B200NB_EINVAL, "id128 is NULL");
+    if (!g_nccl.load()) return fail(nullptr, B200NB_ENCCL, "%s", g_nccl.err.c_str());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, B200NB_ENCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(id128, &id, sizeof id);
+    return B200NB_OK;
+}
+
+void b200nb_destroy(b200nb_ctx *c)
+{
+    if (!c) return;
+    DeviceGuard guard;
+    for (auto &s : c->shards) {
+        if (cudaSetDevice(s.device) != cudaSuccess) continue;
+        if (s.s_compute) cudaStreamSynchronize(s.s_compute);
+        if (s.s_comm) cudaStreamSynchronize(s.s_comm);
+        if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
+        for (auto e : s.prof) cudaEventDestroy(e);
+        cudaFree(s.bodies); cudaFree(s.vel); cudaFree(s.acc); cudaFree(s.mass); cudaFree(s.partial); cudaFree(s.stage);
+        cudaFree(s.energy_blocks); cudaFree(s.energy_out); cudaFree(s.l2_scratch);
+        for (auto t : s.timer) if (t) cudaEventDestroy(t);
+        if (s.ev_integrated) cudaEventDestroy(s.ev_integrated);
+        if (s.ev_gathered) cudaEventDestroy(s.ev_gathered);
+        if (s.s_compute) cudaStreamDestroy(s.s_compute);
+        if (s.s_comm) cudaStreamDestroy(s.s_comm);
+    }
+    delete c;
+}
+
+const char *b200nb_last_error(const b200nb_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int b200nb_upload(b200nb_ctx *c, const float *qx, const float *qy, const float *qz, const float *m, const float *vx,
+                  const float *vy, const float *vz)
+{
+    if (!c) return B200NB_EINVAL;
+    if (!qx || !qy || !qz || !m || !vx || !vy || !vz) return fail(c, B200NB_EINVAL, "upload: NULL array");
+    DeviceGuard guard;
+    const float *src[7] = {qx, qy, qz, m, vx, vy, vz};
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        // the previous step's gather may still be writing remote slices of `bodies`
+        CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0));
+        for (int k = 0; k < 7; ++k)
+            CU(c, cudaMemcpyAsync(s.stage + (size_t)k * c->stage_stride, src[k], c->n * 4, cudaMemcpyHostToDevice, s.s_compute));
+        const int grid = (int)std::min<uint64_t>((c->total_pad + 255) / 256, (uint64_t)s.n_sms * 8);
+        pack_kernel<<<grid, 256, 0, s.s_compute>>>(s.stage, c->stage_stride, c->n, c->total_pad, c->G, s.bodies, s.vel,
+                                                  s.mass, c->L, (uint64_t)s.rank * c->L);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    // host pointers are only borrowed for the call: the copies must have left them (pinned memory is truly async)
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        CU(c, cudaStreamSynchronize(s.s_compute));
+    }
+    c->uploaded = true;
+    c->acc_valid = false;
+    return B200NB_OK;
+}
+
+int b200nb_download_state(b200nb_ctx *c, float *qx, float *qy, float *qz, float *vx, float *vy, float *vz)
+{
+    if (!c) return B200NB_EINVAL;
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "download_state before upload");
+    DeviceGuard guard;
+    if (int rc = sync_all(c)) return rc;
+    if (qx || qy || qz) {
+        Shard &s = c->shards[0]; // positions are replicated: any shard has all of them after the gather
+        CU(c, cudaSetDevice(s.device));
+        const int grid = (int)std::min<uint64_t>((c->n + 255) / 256, (uint64_t)s.n_sms * 8);
+        unpack_positions_kernel<<<grid, 256, 0, s.s_compute>>>(s.bodies, c->n, s.stage, c->stage_stride);
+        c->launches++;
+        CU(c, cudaGetLastError());
+        float *dst[3] = {qx, qy, qz};
+        for (int k = 0; k < 3; ++k)
+            if (dst[k])
+                CU(c, cudaMemcpyAsync(dst[k], s.stage + (size_t)k * c->stage_stride, c->n * 4, cudaMemcpyDeviceToHost, s.s_compute));
+        CU(c, cudaStreamSynchronize(s.s_compute));
+    }
+    if (vx || vy || vz) return download_sliced(c, &Shard::vel, vx, vy, vz);
+    return B200NB_OK;
+}
+
+int b200nb_download_accel(b200nb_ctx *c, float *ax, float *ay, float *az)
+{
+    if (!c) return B200NB_EINVAL;
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "download_accel before upload");
+    DeviceGuard guard;
+    if (int rc = sync_all(c)) return rc;
+    return download_sliced(c, &Shard::acc, ax, ay, az);
+}
+
+int b200nb_step(b200nb_ctx *c, float dt, int integrator, int n_steps)
+{
+    if (!c) return B200NB_EINVAL;
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "step before upload");
+    if (integrator != B200NB_INTEGRATOR_MURB && integrator != B200NB_INTEGRATOR_LEAPFROG)
+        return fail(c, B200NB_EINVAL, "unknown integrator %d", integrator);
+    if (n_steps < 0) return fail(c, B200NB_EINVAL, "n_steps < 0");
+    DeviceGuard guard;
+    for (int it = 0; it < n_steps; ++it) {
+        if (integrator == B200NB_INTEGRATOR_MURB) {
+            if (int rc = enqueue_force(c)) return rc;
+            if (int rc = enqueue_integrate(c, IM_MURB, dt)) return rc;
+            if (int rc = enqueue_gather(c)) return rc;
+            c->acc_valid = false; // acc belongs to the positions before the update
+        } else {
+            if (!c->acc_valid) { // a(x_0): once after an upload
+                if (int rc = enqueue_force(c)) return rc;
+                if (int rc = enqueue_integrate(c, IM_REDUCE_ONLY, dt)) return rc;
+            }
+            if (int rc = enqueue_integrate(c, IM_LF_KICK_DRIFT, dt)) return rc;
+            if (int rc = enqueue_gather(c)) return rc;
+            if (int rc = enqueue_force(c)) return rc;
+            if (int rc = enqueue_integrate(c, IM_LF_KICK, dt)) return rc;
+            c->acc_valid = true; // acc == a(x_{n+1})
+        }
+    }
+    return B200NB_OK;
+}
+
+int b200nb_accel(b200nb_ctx *c)
+{
+    if (!c) return B200NB_EINVAL;
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "accel before upload");
+    DeviceGuard guard;
+    if (int rc = enqueue_force(c)) return rc;
+    if (int rc = enqueue_integrate(c, IM_REDUCE_ONLY, 0.f)) return rc;
+    c->acc_valid = true;
+    return B200NB_OK;
+}
+
+int b200nb_integrate_host_accel(b200nb_ctx *c, const float *ax, const float *ay, const float *az, float dt)
+{
+    if (!c) return B200NB_EINVAL;
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "integrate before upload");
+    if (!ax || !ay || !az) return fail(c, B200NB_EINVAL, "integrate_host_accel: NULL array");
+    DeviceGuard guard;
+    const float *src[3] = {ax, ay, az};
+    for (auto &s : c->shards) {
+        if (s.n_local == 0) continue;
+        CU(c, cudaSetDevice(s.device));
+        for (int k = 0; k < 3; ++k)
+            CU(c, cudaMemcpyAsync(s.stage + (size_t)k * c->stage_stride, src[k], c->n * 4, cudaMemcpyHostToDevice, s.s_compute));
+        load_acc_kernel<<<(s.n_local + 255) / 256, 256, 0, s.s_compute>>>(s.stage, c->stage_stride, (uint64_t)s.rank * c->L,
+                                                                       s.n_local, s.acc, c->L);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
+    if (int rc = enqueue_integrate(c, IM_MURB_STORED, dt)) return rc;
+    if (int rc = enqueue_gather(c)) return rc;
+    c->acc_valid = false;
+    return sync_all(c); // borrowed host pointers (see upload)
+}
+
+int b200nb_energy(b200nb_ctx *c, double *total)
+{
+    if (!c || !total) return B200NB_EINVAL;
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "energy before upload");
+    DeviceGuard guard;
+    if (int rc = sync_all(c)) return rc; // positions gathered, velocities final
+    double sum = 0.0;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        const uint32_t nb = (s.n_local + ENERGY_THREADS - 1) / ENERGY_THREADS;
+        double e = 0.0;
+        if (nb > 0) {
+            energy_kernel<<<nb, ENERGY_THREADS, 0, s.s_compute>>>(s.bodies, s.vel, s.mass, (uint32_t)c->L, s.n_local,
+                                                                 (uint64_t)s.rank * c->L, c->nblk_total, c->soft2,
+                                                                 s.energy_blocks);
+            energy_final_kernel<<<1, 256, 0, s.s_compute>>>(s.energy_blocks, nb, s.energy_out);
+            c->launches += 2;
+            CU(c, cudaGetLastError());
+        } else {
+            CU(c, cudaMemsetAsync(s.energy_out, 0, 8, s.s_compute));
+        }
+        if (c->shards.size() != (size_t)c->n_ranks) // one rank per process: sum over ranks on the device
+            NC(c, g_nccl.AllReduce(s.energy_out, s.energy_out, 1, ncclDouble, ncclSum, s.comm, s.s_compute));
+        CU(c, cudaMemcpyAsync(&e, s.energy_out, 8, cudaMemcpyDeviceToHost, s.s_compute));
+        CU(c, cudaStreamSynchronize(s.s_compute));
+        sum += e;
+    }
+    *total = sum;
+    return B200NB_OK;
+}
+
+int b200nb_sync(b200nb_ctx *c)
+{
+    if (!c) return B200NB_EINVAL;
+    DeviceGuard guard;
+    return sync_all(c);
+}
+
+uint64_t b200nb_slice_length(uint64_t n_bodies, int n_ranks)
+{
+    if (n_ranks < 1) return 0;
+    const uint64_t per = (n_bodies + n_ranks - 1) / n_ranks;
+    return (per + SLICE_ALIGN - 1) / SLICE_ALIGN * SLICE_ALIGN;
+}
+uint64_t b200nb_n_bodies(const b200nb_ctx *c) { return c ? c->n : 0; }
+int b200nb_n_local_gpus(const b200nb_ctx *c) { return c ? (int)c->shards.size() : 0; }
+uint64_t b200nb_allocated_bytes(const b200nb_ctx *c)
+{
+    uint64_t b = 0;
+    if (c) for (auto &s : c->shards) b += s.bytes;
+    return b;
+}
+uint64_t b200nb_launch_count(const b200nb_ctx *c) { return c ? c->launches : 0; }
+const char *b200nb_kernel_name(const b200nb_ctx *c) { return c ? c->kv->name : ""; }
+
+int b200nb_event_record(b200nb_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= N_TIMER_SLOTS) return B200NB_EINVAL;
+    DeviceGuard guard;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        CU(c, cudaEventRecord(s.timer[slot], s.s_compute));
+    }
+    return B200NB_OK;
+}
+
+int b200nb_event_elapsed_ms(b200nb_ctx *c, int a, int b, float *ms)
+{
+    if (!c || !ms || a < 0 || b < 0 || a >= N_TIMER_SLOTS || b >= N_TIMER_SLOTS) return B200NB_EINVAL;
+    DeviceGuard guard;
+    float mx = 0.f;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        CU(c, cudaEventSynchronize(s.timer[b]));
+        float t = 0.f;
+        CU(c, cudaEventElapsedTime(&t, s.timer[a], s.timer[b]));
+        mx = std::max(mx, t);
+    }
+    *ms = mx;
+    return B200NB_OK;
+}
+
+int b200nb_profile_enable(b200nb_ctx *c, int on)
+{
+    if (!c) return B200NB_EINVAL;
+    DeviceGuard guard;
+    if (int rc = sync_all(c)) return rc;
+    for (auto &s : c->shards) {
+        for (auto e : s.prof) cudaEventDestroy(e);
+        s.prof.clear();
+    }
+    c->profiling = on != 0;
+    return B200NB_OK;
+}
+
+int b200nb_profile_get(b200nb_ctx *c, double *force_ms_total, uint64_t *force_launches)
+{
+    if (!c) return B200NB_EINVAL;
+    DeviceGuard guard;
+    if (int rc = sync_all(c)) return rc;
+    double mx = 0.0;
+    uint64_t n = 0;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        double t = 0.0;
+        for (size_t i = 0; i + 1 < s.prof.size(); i += 2) {
+            float ms = 0.f;
+            CU(c, cudaEventElapsedTime(&ms, s.prof[i], s.prof[i + 1]));
+            t += ms;
+        }
+        mx = std::max(mx, t);
+        n = std::max<uint64_t>(n, s.prof.size() / 2);
+    }
+    if (force_ms_total) *force_ms_total = mx;
+    if (force_launches) *force_launches = n;
+    return B200NB_OK;
+}
+
+int b200nb_flush_l2(b200nb_ctx *c)
+{
+    if (!c) return B200NB_EINVAL;
+    DeviceGuard guard;
+    constexpr size_t bytes = 256ull << 20;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        if (!s.l2_scratch) CU(c, cudaMalloc(&s.l2_scratch, bytes));
+        CU(c, cudaMemsetAsync(s.l2_scratch, 0x5a, bytes, s.s_compute));
+    }
+    return B200NB_OK;
+}
+
+int b200nb_host_alloc(void **ptr, uint64_t bytes)
+{
+    if (!ptr) return B200NB_EINVAL;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, B200NB_ECUDA, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return B200NB_OK;
+}
+
+int b200nb_host_free(void *ptr)
+{
+    if (!ptr) return B200NB_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? B200NB_OK : B200NB_ECUDA;
+}
+
+} // extern "C"

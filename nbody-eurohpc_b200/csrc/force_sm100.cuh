@@ -124,9 +124,11 @@ struct ForceArgs {
     float *partial;              // [rows][3][tgt_stride] partial accelerations
     uint32_t tgt_blk0;           // first target block inside `tgt`
     uint32_t tgt_stride;         // floats per component row of `partial` (padded local target count)
-    uint32_t src_blk0, src_nblk; // source block range of this launch
-    uint32_t n_chunks;           // source chunks of this launch (== gridDim.y)
-    uint32_t row0;               // first partial row this launch writes
+    uint32_t src_nblk_total;     // AoSoA blocks in the whole padded system (sources)
+    uint32_t n_chunks_total;     // S: source chunks the system is cut into (a multiple of the rank count)
+    uint32_t chunk_first;        // first LOGICAL chunk of this launch; gridDim.y chunks are processed
+    uint32_t chunk_rot;          // logical -> physical chunk rotation, (logical + rot) % S.  rot = k*rank makes
+                                 // logical chunks [0,k) the rank's own slice (resident before the all-gather)
     float soft2;
     unsigned long long *dbg;     // optional: per-CTA {clock64 start,end, globaltimer start,end}
 };
@@ -249,10 +251,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns0));
     }
 
-    // balanced split of the source blocks over the chunks of this launch
-    const uint32_t c = blockIdx.y;
-    const uint32_t b_begin = a.src_blk0 + (uint32_t)(((uint64_t)a.src_nblk * c) / a.n_chunks);
-    const uint32_t b_end = a.src_blk0 + (uint32_t)(((uint64_t)a.src_nblk * (c + 1)) / a.n_chunks);
+    // balanced split of the source blocks over the S chunks; partial row = logical chunk index
+    const uint32_t c = a.chunk_first + blockIdx.y;
+    const uint32_t pc = (c + a.chunk_rot) % a.n_chunks_total;
+    const uint32_t b_begin = (uint32_t)(((uint64_t)a.src_nblk_total * pc) / a.n_chunks_total);
+    const uint32_t b_end = (uint32_t)(((uint64_t)a.src_nblk_total * (pc + 1)) / a.n_chunks_total);
     const uint32_t nblk = b_end - b_begin;
     const uint32_t ntiles = (nblk + TJB - 1) / TJB;
     const float *chunk_src = a.src + (size_t)b_begin * BLK_FLOATS;
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
         }
     }
 
-    const size_t row = (size_t)(a.row0 + c) * 3;
+    const size_t row = (size_t)c * 3;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         const size_t il = (size_t)blockIdx.x * TI + (size_t)k * THREADS + threadIdx.x;

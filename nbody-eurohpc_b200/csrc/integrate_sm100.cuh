@@ -1,0 +1,218 @@
+// O(N) kernels around the force pass: layout pack/unpack, the fused partial-sum reduction + integrator, energy.
+//
+// Replaces, from scratch:
+//   devUpdatePositionsAndVelocities           src/common/core/CUDABodies.cu:125-153   (MUrB explicit scheme)
+//   devLeapfrogFirst/Middle/Last + dispatcher src/common/core/CUDABodies.cu:215-347   (documented intent :172-211)
+//   devInitializeDevGM                        src/murb/implem/SimulationNBodyCUDATileFullDevice.cu:41-45
+//   devComputeBodiesMetrics + cub::DeviceReduce::Sum
+//                                             src/murb/implem/SimulationNBodyCUDAPropertyTracking.cu:217-304,333-364
+// All of them are HBM-bound streaming kernels (coalesced, a few dozen bytes per body) and run in microseconds; they
+// are fused so one step is: force pass -> one integrator kernel.
+#pragma once
+#include "force_sm100.cuh"
+
+namespace b200nb {
+
+enum IntegrateMode : int {
+    IM_REDUCE_ONLY = 0,  // acc = sum of partial rows
+    IM_MURB = 1,         // acc = sum of partial rows; q += (v + a*dt/2)*dt; v += a*dt      (Bodies.cpp:259-278)
+    IM_LF_KICK_DRIFT = 2,// uses stored acc: v += a*dt/2; q += v*dt                         (leapfrog first half)
+    IM_LF_KICK = 3,      // acc = sum of partial rows; v += a*dt/2                          (leapfrog closing kick)
+    IM_MURB_STORED = 4   // MUrB update with the stored acc (caller-supplied accelerations)
+};
+
+struct IntegrateArgs {
+    float *bodies;        // blocked full array; the slice [first, first+L) is updated in place
+    float *vel;           // [3][L] local velocities
+    float *acc;           // [3][L] local accelerations
+    const float *partial; // [rows][3][L]
+    uint32_t rows;
+    uint32_t L;           // local slice length == row stride
+    uint32_t n_local;     // real (non-padding) bodies in the slice
+    uint64_t first;       // global index of the first local body (multiple of BLK)
+    float dt;
+    int mode;
+};
+
+__global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_local) return;
+    const size_t L = a.L;
+
+    float ax, ay, az;
+    if (a.mode == IM_LF_KICK_DRIFT || a.mode == IM_MURB_STORED) {
+        ax = a.acc[i]; ay = a.acc[L + i]; az = a.acc[2 * L + i];
+    } else {
+        // fixed-order fp64 sum of the chunk partials: deterministic, and the top level of the
+        // hierarchical summation that keeps the fp32 error independent of N
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (uint32_t r = 0; r < a.rows; ++r) {
+            const float *p = a.partial + (size_t)r * 3 * L;
+            sx += (double)p[i]; sy += (double)p[L + i]; sz += (double)p[2 * L + i];
+        }
+        ax = (float)sx; ay = (float)sy; az = (float)sz;
+        a.acc[i] = ax; a.acc[L + i] = ay; a.acc[2 * L + i] = az;
+        if (a.mode == IM_REDUCE_ONLY) return;
+    }
+
+    float vx = a.vel[i], vy = a.vel[L + i], vz = a.vel[2 * L + i];
+    const size_t g = a.first + i;
+    const size_t ix = blk_index(g, 0), iy = blk_index(g, 1), iz = blk_index(g, 2);
+
+    if (a.mode == IM_MURB || a.mode == IM_MURB_STORED) {
+        // The reference writes `q + (v + aDt * 0.5) * dt` with a double literal, so for T=float the position update
+        // is evaluated in fp64 and rounded once (Bodies.cpp:264-270, CUDABodies.cu:139-141).  Same here, without
+        // FMA contraction so the result is bit-identical to the host restatement in oracle/.
+        const float axdt = __fmul_rn(ax, a.dt), aydt = __fmul_rn(ay, a.dt), azdt = __fmul_rn(az, a.dt);
+        const double dt = (double)a.dt;
+        const double qx = (double)a.bodies[ix], qy = (double)a.bodies[iy], qz = (double)a.bodies[iz];
+        a.bodies[ix] = (float)__dadd_rn(qx, __dmul_rn(__dadd_rn((double)vx, __dmul_rn((double)axdt, 0.5)), dt));
+        a.bodies[iy] = (float)__dadd_rn(qy, __dmul_rn(__dadd_rn((double)vy, __dmul_rn((double)aydt, 0.5)), dt));
+        a.bodies[iz] = (float)__dadd_rn(qz, __dmul_rn(__dadd_rn((double)vz, __dmul_rn((double)azdt, 0.5)), dt));
+        a.vel[i] = __fadd_rn(vx, axdt);
+        a.vel[L + i] = __fadd_rn(vy, aydt);
+        a.vel[2 * L + i] = __fadd_rn(vz, azdt);
+        return;
+    }
+
+    // leapfrog half kick (both modes)
+    const float hdt = __fmul_rn(a.dt, 0.5f);
+    vx = __fmaf_rn(ax, hdt, vx);
+    vy = __fmaf_rn(ay, hdt, vy);
+    vz = __fmaf_rn(az, hdt, vz);
+    a.vel[i] = vx; a.vel[L + i] = vy; a.vel[2 * L + i] = vz;
+    if (a.mode == IM_LF_KICK_DRIFT) { // drift, fp64 like the MUrB position update
+        const double dt = (double)a.dt;
+        a.bodies[ix] = (float)__fma_rn((double)vx, dt, (double)a.bodies[ix]);
+        a.bodies[iy] = (float)__fma_rn((double)vy, dt, (double)a.bodies[iy]);
+        a.bodies[iz] = (float)__fma_rn((double)vz, dt, (double)a.bodies[iz]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- pack / unpack
+// stage: 7 host-layout SoA arrays (qx qy qz m vx vy vz), each `stride` floats.  Builds the blocked array for ALL
+// total_pad bodies (padding: G*m = 0 at the position of the last real body, so it adds exactly 0 and cannot create
+// a singularity that a real pair does not have) and the local slice of velocities and masses.
+__global__ void __launch_bounds__(256) pack_kernel(const float *__restrict__ stage, size_t stride, size_t n,
+                                                  size_t total_pad, float G, float *__restrict__ bodies,
+                                                  float *__restrict__ vel, float *__restrict__ mass, size_t L,
+                                                  size_t first)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pad; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = i < n ? i : n - 1;
+        const float m = i < n ? stage[3 * stride + i] : 0.f;
+        bodies[blk_index(i, 0)] = stage[s];
+        bodies[blk_index(i, 1)] = stage[stride + s];
+        bodies[blk_index(i, 2)] = stage[2 * stride + s];
+        bodies[blk_index(i, 3)] = __fmul_rn(G, m); // devInitializeDevGM: GM[i] = G * m[i]
+        if (i >= first && i < first + L) {
+            const size_t li = i - first;
+            const bool real = i < n;
+            vel[li] = real ? stage[4 * stride + i] : 0.f;
+            vel[L + li] = real ? stage[5 * stride + i] : 0.f;
+            vel[2 * L + li] = real ? stage[6 * stride + i] : 0.f;
+            mass[li] = m;
+        }
+    }
+}
+
+// blocked positions -> three SoA arrays of `stride` floats (all n bodies; positions are replicated on every GPU)
+__global__ void __launch_bounds__(256) unpack_positions_kernel(const float *__restrict__ bodies, size_t n,
+                                                              float *__restrict__ stage, size_t stride)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        stage[i] = bodies[blk_index(i, 0)];
+        stage[stride + i] = bodies[blk_index(i, 1)];
+        stage[2 * stride + i] = bodies[blk_index(i, 2)];
+    }
+}
+
+// load caller-supplied accelerations (host SoA staged at `stage`, 3 x stride) into the local acc slice
+__global__ void __launch_bounds__(256) load_acc_kernel(const float *__restrict__ stage, size_t stride, size_t first,
+                                                      uint32_t n_local, float *__restrict__ acc, size_t L)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_local) return;
+    acc[i] = stage[first + i];
+    acc[L + i] = stage[stride + first + i];
+    acc[2 * L + i] = stage[2 * stride + first + i];
+}
+
+// ---------------------------------------------------------------------------------------------- energy
+// E_i = m_i |v_i|^2 / 2  -  (m_i / 2) * ( sum_j Gm_j / sqrt(r_ij^2 + soft^2)  -  Gm_i / soft )
+// (definition and self-term handling: SimulationNBodyCUDAPropertyTracking.cu:262-301).  The pair sum uses
+// rsqrt.approx + one Newton step (~1e-7 relative), 128-term fp32 tile sums and an fp64 running sum.
+constexpr int ENERGY_THREADS = 128;
+
+__device__ __forceinline__ float rsqrt_nr(float d)
+{
+    const float y = rsqrt_approx(d);
+    return y * fmaf(-0.5f * d, y * y, 1.5f);
+}
+
+__global__ void __launch_bounds__(ENERGY_THREADS) energy_kernel(const float *__restrict__ bodies,
+                                                                const float *__restrict__ vel,
+                                                                const float *__restrict__ mass, uint32_t L,
+                                                                uint32_t n_local, uint64_t first, uint32_t nblk_total,
+                                                                float soft2, double *__restrict__ block_out)
+{
+    __shared__ __align__(16) float tile[BLK_FLOATS];
+    __shared__ double warp_sums[ENERGY_THREADS / 32];
+    const uint32_t i = blockIdx.x * ENERGY_THREADS + threadIdx.x;
+    const bool valid = i < n_local;
+    const size_t g = first + (valid ? i : 0);
+    const float xi = bodies[blk_index(g, 0)], yi = bodies[blk_index(g, 1)], zi = bodies[blk_index(g, 2)];
+    const float gi = bodies[blk_index(g, 3)];
+
+    double pot = 0.0;
+    for (uint32_t b = 0; b < nblk_total; ++b) {
+        __syncthreads();
+        reinterpret_cast<float4 *>(tile)[threadIdx.x] =
+            reinterpret_cast<const float4 *>(bodies + (size_t)b * BLK_FLOATS)[threadIdx.x];
+        __syncthreads();
+        float s = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < BLK; ++j) {
+            const float dx = tile[j] - xi, dy = tile[BLK + j] - yi, dz = tile[2 * BLK + j] - zi;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, soft2)));
+            s = fmaf(tile[3 * BLK + j], rsqrt_nr(d), s);
+        }
+        pot += (double)s;
+    }
+    double e = 0.0;
+    if (valid) {
+        const float vx = vel[i], vy = vel[L + i], vz = vel[2 * (size_t)L + i];
+        const double m = (double)mass[i];
+        const double self = (double)gi * (double)rsqrt_nr(soft2);
+        const double v2 = (double)vx * vx + (double)vy * vy + (double)vz * vz;
+        e = 0.5 * m * v2 - 0.5 * m * (pot - self);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < ENERGY_THREADS / 32; ++w) t += warp_sums[w];
+        block_out[blockIdx.x] = t;
+    }
+}
+
+// fixed-order final sum (deterministic; replaces cub::DeviceReduce::Sum and its per-call cudaMalloc)
+__global__ void __launch_bounds__(256) energy_final_kernel(const double *__restrict__ block_out, uint32_t nb,
+                                                          double *__restrict__ out)
+{
+    __shared__ double sh[256];
+    double t = 0.0;
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) t += block_out[k];
+    sh[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+} // namespace b200nb

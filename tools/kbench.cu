@@ -308,7 +308,7 @@ int main(int argc, char **argv)
         ForceArgs a{};
         a.src = p.d_bodies; a.tgt = p.d_bodies; a.partial = p.d_partial;
         a.tgt_blk0 = 0; a.tgt_stride = (uint32_t)p.n_pad;
-        a.src_blk0 = 0; a.src_nblk = n_blocks; a.n_chunks = plan.n_chunks; a.row0 = 0;
+        a.src_nblk_total = n_blocks; a.n_chunks_total = plan.n_chunks; a.chunk_first = 0; a.chunk_rot = 0;
         a.soft2 = p.soft2;
         dim3 grid(n_itiles, plan.n_chunks);
         const size_t ctas = (size_t)n_itiles * plan.n_chunks;
