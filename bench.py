@@ -207,17 +207,13 @@ def run_b200_arm(args, rank, world, local_rank):
     import torch
     import b200nb
 
-    dist = None
+    from b200nb import dist as bdist
+
+    dist = bdist.init_process_group()     # None for a single rank
     nccl_id = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
-        box = [b200nb.Context.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        nccl_id = box[0]
-    else:
-        torch.cuda.set_device(local_rank)
+    if dist is not None:
+        nccl_id = bdist.broadcast_bytes(dist, b200nb.Context.unique_id() if rank == 0 else None)
+    torch.cuda.set_device(local_rank)
     torch.cuda.init()
     n = args.bodies
     bodies = b200nb.init_bodies(args.scheme, n)

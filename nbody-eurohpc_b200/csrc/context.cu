@@ -74,15 +74,16 @@ struct KernelVariant {
     int threads, r, tjb, st;
     size_t smem;
 };
-#define VARIANT(NAME, THREADS, R, TJB, ST, PACKED, WP, U, MINB)                                                        \
-    KernelVariant { NAME, force_kernel<THREADS, R, TJB, ST, PACKED, WP, U, MINB>, THREADS, R, TJB, ST,                 \
+#define VARIANT(NAME, THREADS, R, TJB, ST, MATH, WP, U, MINB)                                                        \
+    KernelVariant { NAME, force_kernel<THREADS, R, TJB, ST, MATH, WP, U, MINB>, THREADS, R, TJB, ST,                 \
                     force_smem_bytes<THREADS, R, TJB, ST, WP>() }
 const KernelVariant g_variants[] = {
     // default first; chosen from the B200 sweep in profiles/ (tools/kbench)
-    VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, true, false, 2, 3),
-    VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, true, false, 1, 2),
-    VARIANT("pk_t256_r4_tj4_st2_cta_u2_mb2", 256, 4, 4, 2, true, false, 2, 2),
-    VARIANT("sc_t256_r4_tj2_st3_cta_u1_mb2", 256, 4, 2, 3, false, false, 1, 2),
+    VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3),
+    VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, false, 1, 2),
+    VARIANT("pk_t256_r4_tj4_st2_cta_u2_mb2", 256, 4, 4, 2, 1, false, 2, 2),
+    VARIANT("sc_t256_r4_tj2_st3_cta_u1_mb2", 256, 4, 2, 3, 0, false, 1, 2),
+    VARIANT("ps_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 2, false, 2, 3),
 };
 constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr uint64_t SLICE_ALIGN = 1024; // multiple of THREADS*R of every variant and of BLK

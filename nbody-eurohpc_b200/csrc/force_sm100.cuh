@@ -140,8 +140,23 @@ constexpr size_t force_smem_bytes()
 }
 
 // ------------------------------------------------------------------------------------------- inner math
+// acc += f * d on a packed pair.  SCALAR_ACC issues it as two scalar FFMA: an FFMA2 whose three 64-bit operands are
+// all distinct needs three register-file reads per lane pair, and the B200 sweep (profiles/) shows those
+// accumulate instructions are where the FMA pipe loses cycles; two FFMA cost the same pipe time (2 x 1 clk) and the
+// spare issue slots are free in the packed regime.
+template <bool SCALAR_ACC>
+__device__ __forceinline__ uint64_t acc_fma(uint64_t f, uint64_t d, uint64_t acc)
+{
+    if (!SCALAR_ACC) return fma2(f, d, acc);
+    float f0, f1, d0, d1, a0, a1;
+    upk2(f, f0, f1);
+    upk2(d, d0, d1);
+    upk2(acc, a0, a1);
+    return pk2(fmaf(f0, d0, a0), fmaf(f1, d1, a1));
+}
+
 // One AoSoA block (128 sources) against R register-blocked targets, packed f32x2 along the sources.
-template <int R, int U>
+template <int R, int U, bool SCALAR_ACC>
 __device__ __forceinline__ void block_packed(const float *__restrict__ sb, const float (&xi)[R], const float (&yi)[R],
                                              const float (&zi)[R], uint64_t soft2p, uint64_t (&ax)[R],
                                              uint64_t (&ay)[R], uint64_t (&az)[R])
@@ -172,9 +187,9 @@ __device__ __forceinline__ void block_packed(const float *__restrict__ sb, const
                 const uint64_t gi = mul2(gj, inv);
                 const uint64_t i2 = mul2(inv, inv);
                 const uint64_t f = mul2(i2, gi);
-                ax[k] = fma2(f, dx, ax[k]);
-                ay[k] = fma2(f, dy, ay[k]);
-                az[k] = fma2(f, dz, az[k]);
+                ax[k] = acc_fma<SCALAR_ACC>(f, dx, ax[k]);
+                ay[k] = acc_fma<SCALAR_ACC>(f, dy, ay[k]);
+                az[k] = acc_fma<SCALAR_ACC>(f, dz, az[k]);
             }
         }
     }
@@ -223,11 +238,11 @@ __device__ __forceinline__ void block_scalar(const float *__restrict__ sb, const
 // R            targets per thread (register blocking)
 // TJB          AoSoA blocks (of 128 sources) per pipeline stage
 // ST           pipeline stages
-// PACKED       f32x2 instructions (true) or scalar FP32 (false)
+// MATH         0 = scalar FP32, 1 = packed f32x2, 2 = packed f32x2 with scalar-FFMA accumulation
 // WARP_PRIVATE each warp owns its stages and barriers (no CTA-wide barrier in the loop)
 // U            unroll of the 4-source inner step
 // MINB         min resident CTAs per SM for __launch_bounds__
-template <int THREADS, int R, int TJB, int ST, bool PACKED, bool WARP_PRIVATE, int U, int MINB>
+template <int THREADS, int R, int TJB, int ST, int MATH, bool WARP_PRIVATE, int U, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
 {
     constexpr int TI = THREADS * R;
@@ -304,11 +319,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
         const float *sb = my_stages + (size_t)s * STAGE_FLOATS;
         const uint32_t nb = min((uint32_t)TJB, nblk - t * TJB);
 
-        if (PACKED) {
+        if (MATH != 0) {
             uint64_t ax[R], ay[R], az[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) ax[k] = ay[k] = az[k] = 0ull;
-            for (uint32_t b = 0; b < nb; ++b) block_packed<R, U>(sb + b * BLK_FLOATS, xi, yi, zi, soft2p, ax, ay, az);
+            for (uint32_t b = 0; b < nb; ++b) block_packed<R, U, MATH == 2>(sb + b * BLK_FLOATS, xi, yi, zi, soft2p, ax, ay, az);
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 float lo, hi;

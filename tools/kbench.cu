@@ -30,12 +30,18 @@ using namespace b200nb;
 template <int KIND, int ILP> // 0 FFMA, 1 FFMA2, 2 MUFU.RSQ, 3 FADD2 (broadcast operand), 4 FMUL2, 5 mix 12 f32x2 + 2 mufu
 __global__ void __launch_bounds__(256) ubench(float *out, unsigned long long *cyc, int iters, float seed)
 {
-    float v[ILP];
-    uint64_t p[ILP];
+    __shared__ __align__(16) float sm[256];
+    sm[threadIdx.x] = seed * threadIdx.x;
+    float v[ILP], y[ILP], z2[ILP], z = seed;
+    uint64_t p[ILP], q[ILP], w[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; ++i) {
         v[i] = seed + threadIdx.x * 1e-3f + i;
+        y[i] = v[i] * 0.5f;
+        z2[i] = 0.99f + 1e-4f * threadIdx.x + 1e-5f * i;
         p[i] = pk2(v[i], v[i] + 0.5f);
+        q[i] = pk2(v[i] * 1e-3f, v[i] * 2e-3f + out[i]);
+        w[i] = pk2(0.999f + out[threadIdx.x + i + 8], 0.998f - out[threadIdx.x + i + 16]);
     }
     const float c1 = seed * 0.999f, c2 = seed * 1e-3f;
     const uint64_t pc1 = pk2(c1, c1), pc2 = pk2(c2, c2);
@@ -51,6 +57,19 @@ __global__ void __launch_bounds__(256) ubench(float *out, unsigned long long *cy
                 if (KIND == 2) v[i] = rsqrt_approx(v[i]);
                 if (KIND == 3) p[i] = sub2(p[i], pk2(c2, c2));
                 if (KIND == 4) p[i] = mul2(p[i], pc1);
+                if (KIND == 6) p[i] = fma2(q[i], w[i], p[i]);          // 3 distinct, per-chain 64-bit operands
+                if (KIND == 7) { p[i] = fma2(p[i], pc1, pc2); if ((u % 6) == 5) v[i] = rsqrt_approx(v[i]); } // 6 FFMA2 : 1 MUFU
+                if (KIND == 8) { v[i] = fmaf(v[i], c1, c2); if ((u % 8) == 7 && i == 0) z = rsqrt_approx(z); } // FFMA + rare MUFU
+                if (KIND == 9) { float lo, hi, a0, a1; upk2(q[i], lo, hi); upk2(w[i], a0, a1);      // scalar accumulate of a pair
+                                 v[i] = fmaf(lo, a0, v[i]); y[i] = fmaf(hi, a1, y[i]); }
+                if (KIND == 10) { p[i] = fma2(p[i], pc1, pc2); if ((u % 4) == 3 && i == 0) { float4 t = *(const float4 *)&sm[(it & 31) * 4]; z += t.x; } }
+                if (KIND == 11) p[i] = fma2(q[i], q[i], p[i]);         // 2 distinct pairs
+                if (KIND == 12) p[i] = sub2(q[i], pk2(c2, c2));        // FADD2 broadcast, non-dependent
+                if (KIND == 13) p[i] = fma2(w[i / 3], q[i], p[i]);     // accumulate pattern: groups of 3 share operand A
+                if (KIND == 14) v[i] = fmaf(y[i], z2[i], v[i]);        // scalar FFMA, 3 distinct vector registers
+                if (KIND == 15) p[i] = fma2(q[i], q[i], pk2(y[i], y[i])); // 1 pair + scalar broadcast addend (non-dependent)
+                if (KIND == 16) p[i] = sub2(p[i], pk2(y[i], y[i]));    // FADD2 pair - broadcast vector scalar
+                if (KIND == 17) p[i] = mul2(q[i], p[i]);               // FMUL2 2 distinct pairs
                 if (KIND == 5) { // same op mix as one packed interaction pair, fully dependent inside a chain
                     uint64_t dx = sub2(p[i], pc2), dy = sub2(p[i], pc1), dz = sub2(pc1, p[i]);
                     uint64_t d = fma2(dx, dx, pc2);
@@ -73,8 +92,9 @@ __global__ void __launch_bounds__(256) ubench(float *out, unsigned long long *cy
     for (int i = 0; i < ILP; ++i) {
         float lo, hi;
         upk2(p[i], lo, hi);
-        acc += v[i] + lo + hi;
+        acc += v[i] + lo + hi + y[i];
     }
+    acc += z;
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -87,6 +107,7 @@ static void run_ubench(const char *name, int ctas_per_sm, int sms, double instr_
     float *out;
     unsigned long long *cyc;
     CK(cudaMalloc(&out, (size_t)grid * threads * 4));
+    CK(cudaMemset(out, 0, (size_t)grid * threads * 4));
     CK(cudaMalloc(&cyc, (size_t)grid * 8));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -145,15 +166,15 @@ struct Variant {
 
 static std::vector<Variant> g_variants;
 
-template <int THREADS, int R, int TJB, int ST, bool PACKED, bool WP, int U, int MINB> static void reg_variant()
+template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MINB> static void reg_variant()
 {
     Variant v;
     char nm[128];
-    snprintf(nm, sizeof nm, "%s_t%d_r%d_tj%d_st%d_%s_u%d_mb%d", PACKED ? "pk" : "sc", THREADS, R, TJB, ST,
+    snprintf(nm, sizeof nm, "%s_t%d_r%d_tj%d_st%d_%s_u%d_mb%d", MATH == 0 ? "sc" : (MATH == 1 ? "pk" : "ps"), THREADS, R, TJB, ST,
              WP ? "warp" : "cta", U, MINB);
     v.name = nm;
-    v.threads = THREADS; v.r = R; v.tjb = TJB; v.st = ST; v.packed = PACKED; v.warp_private = WP; v.u = U; v.minb = MINB;
-    auto k = force_kernel<THREADS, R, TJB, ST, PACKED, WP, U, MINB>;
+    v.threads = THREADS; v.r = R; v.tjb = TJB; v.st = ST; v.packed = MATH; v.warp_private = WP; v.u = U; v.minb = MINB;
+    auto k = force_kernel<THREADS, R, TJB, ST, MATH, WP, U, MINB>;
     v.fn = (const void *)k;
     v.smem = force_smem_bytes<THREADS, R, TJB, ST, WP>();
     v.launch = [k, smem = v.smem](const ForceArgs &a, dim3 grid) {
@@ -165,32 +186,31 @@ template <int THREADS, int R, int TJB, int ST, bool PACKED, bool WP, int U, int 
 
 static void register_all()
 {
-    //            THR  R TJB ST PACK   WP    U MINB
-    reg_variant<256, 4, 2, 3, true, false, 2, 2>();
-    reg_variant<256, 4, 2, 3, true, false, 1, 2>();
-    reg_variant<256, 4, 2, 3, true, false, 4, 2>();
-    reg_variant<256, 2, 2, 3, true, false, 2, 3>();
-    reg_variant<256, 2, 2, 3, true, false, 2, 4>();
-    reg_variant<256, 1, 2, 3, true, false, 2, 4>();
-    reg_variant<256, 8, 2, 3, true, false, 1, 1>();
-    reg_variant<128, 4, 2, 3, true, false, 2, 4>();
-    reg_variant<128, 8, 2, 3, true, false, 1, 2>();
-    reg_variant<128, 8, 2, 3, true, false, 1, 3>();
-    reg_variant<256, 4, 4, 2, true, false, 2, 2>();
-    reg_variant<256, 4, 1, 4, true, false, 2, 2>();
-    reg_variant<256, 4, 1, 3, true, true, 2, 2>();
-    reg_variant<256, 2, 1, 3, true, true, 2, 3>();
-    reg_variant<128, 4, 1, 3, true, true, 2, 4>();
-    reg_variant<512, 2, 2, 3, true, false, 2, 1>();
-    reg_variant<512, 4, 2, 3, true, false, 2, 1>();
-    reg_variant<1024, 1, 2, 3, true, false, 2, 1>();
-    // scalar FP32 comparators (same pipeline, 13 issue slots / interaction)
-    reg_variant<256, 4, 2, 3, false, false, 1, 2>();
-    reg_variant<256, 4, 2, 3, false, false, 2, 2>();
-    reg_variant<256, 8, 2, 3, false, false, 1, 1>();
-    reg_variant<128, 8, 2, 3, false, false, 1, 2>();
-    reg_variant<256, 2, 2, 3, false, false, 2, 4>();
-    reg_variant<256, 4, 1, 3, false, true, 1, 2>();
+    //            THR  R TJB ST MATH  WP    U MINB      MATH: 0 scalar, 1 packed, 2 packed + scalar accumulate
+    reg_variant<256, 2, 2, 3, 1, false, 2, 3>();
+    reg_variant<256, 2, 2, 3, 2, false, 2, 3>();
+    reg_variant<256, 2, 2, 3, 2, false, 1, 3>();
+    reg_variant<256, 2, 2, 3, 2, false, 4, 3>();
+    reg_variant<256, 2, 2, 3, 2, false, 2, 2>();
+    reg_variant<256, 2, 2, 3, 2, false, 2, 4>();
+    reg_variant<256, 1, 2, 3, 2, false, 2, 4>();
+    reg_variant<256, 1, 2, 3, 2, false, 4, 6>();
+    reg_variant<256, 3, 2, 3, 2, false, 2, 2>();
+    reg_variant<256, 4, 2, 3, 2, false, 2, 2>();
+    reg_variant<256, 4, 2, 3, 2, false, 1, 2>();
+    reg_variant<256, 4, 2, 3, 1, false, 2, 2>();
+    reg_variant<128, 4, 2, 3, 2, false, 2, 3>();
+    reg_variant<128, 4, 2, 3, 2, false, 2, 4>();
+    reg_variant<128, 8, 2, 3, 2, false, 1, 2>();
+    reg_variant<128, 8, 2, 3, 1, false, 1, 2>();
+    reg_variant<256, 8, 2, 3, 2, false, 1, 1>();
+    reg_variant<128, 6, 2, 3, 2, false, 1, 2>();
+    reg_variant<512, 2, 2, 3, 2, false, 2, 1>();
+    reg_variant<256, 2, 1, 3, 2, true, 2, 3>();
+    reg_variant<256, 2, 4, 2, 2, false, 2, 3>();
+    reg_variant<256, 2, 1, 4, 2, false, 2, 3>();
+    // scalar FP32 comparator (13 issue slots / interaction)
+    reg_variant<256, 4, 2, 3, 0, false, 1, 2>();
 }
 
 static void make_problem(Problem &p, size_t n, int sms)
@@ -277,6 +297,19 @@ int main(int argc, char **argv)
         run_ubench<3, 8>("FADD2 bcast", 4, sms, 1, jf);
         run_ubench<4, 8>("FMUL2", 4, sms, 1, jf);
         run_ubench<2, 8>("MUFU.RSQ", 4, sms, 1, jf);
+        run_ubench<6, 8>("FFMA2 3 distinct vec pairs", 4, sms, 1, jf);
+        run_ubench<6, 4>("FFMA2 3 distinct vec pairs", 4, sms, 1, jf);
+        run_ubench<13, 6>("FFMA2 acc, 3 share opA", 4, sms, 1, jf);
+        run_ubench<13, 3>("FFMA2 acc, 3 share opA", 4, sms, 1, jf);
+        run_ubench<14, 8>("FFMA 3 distinct vec regs", 4, sms, 1, jf);
+        run_ubench<16, 8>("FADD2 pair - bcast vec", 4, sms, 1, jf);
+        run_ubench<17, 8>("FMUL2 2 distinct pairs", 4, sms, 1, jf);
+        run_ubench<11, 8>("FFMA2 2 distinct pairs", 4, sms, 1, jf);
+        run_ubench<12, 8>("FADD2 bcast indep", 4, sms, 1, jf);
+        run_ubench<9, 8>("2xFFMA scalar acc of pair", 4, sms, 2, jf);
+        run_ubench<7, 8>("6 FFMA2 : 1 MUFU", 4, sms, 1.0 + 1.0 / 6, jf);
+        run_ubench<8, 8>("64 FFMA : 1 MUFU", 4, sms, 1.0 + 1.0 / 64, jf);
+        run_ubench<10, 8>("32 FFMA2 : 1 LDS.128", 4, sms, 1.0 + 1.0 / 32, jf);
         run_ubench<5, 4>("mix 12xf32x2+2xMUFU", 4, sms, 14, jf);
         run_ubench<5, 4>("mix 12xf32x2+2xMUFU", 2, sms, 14, jf);
         run_ubench<5, 2>("mix 12xf32x2+2xMUFU", 4, sms, 14, jf);
