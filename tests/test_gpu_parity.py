@@ -234,10 +234,13 @@ def test_two_gpus_match_one(b200, oracle, integrator):
         with make_ctx(b200, d, n_gpus=g) as ctx:
             ctx.step(DT, integrator, 5)
             outs.append((ctx.download_state(), ctx.download_accel(), ctx.energy()))
+    # different chunking => different (fixed) summation order: agreement to a few fp32 ulps of the system size
+    # (absolute bound: the central body sits at the origin, where a relative bound is meaningless)
+    scale = max(float(np.abs(outs[0][0][c]).max()) for c in ("qx", "qy", "qz"))
     for c in ("qx", "qy", "qz"):
-        assert np.all(within_rel(outs[0][0][c], outs[1][0][c], 1e-6)), c
+        assert np.all(np.abs(outs[0][0][c].astype(np.float64) - outs[1][0][c]) <= 1e-6 * scale), c
     assert max_rel_err(outs[0][1], outs[1][1]) <= 2e-6
-    assert abs(outs[0][2] - outs[1][2]) <= 1e-9 * abs(outs[0][2])
+    assert abs(outs[0][2] - outs[1][2]) <= 1e-6 * abs(outs[0][2])
 
 
 # ------------------------------------------------------------------------------------------------ reference-side binaries
