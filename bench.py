@@ -293,10 +293,17 @@ def run_b200_arm(args, rank, world, local_rank):
     kernel_int_per_s = per_gpu_int_per_launch / (avg_launch_ms * 1e-3)
     achieved_tflops = 2 * PIPE_SLOTS_PER_INTERACTION * kernel_int_per_s / 1e12
     meas_mhz = clocks.get("sm_mhz") or max_mhz
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        t = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+        if t["workload_bodies"] == n and world == 1:
+            traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
         "bound": "fp32_pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / peak_tflops,
-        "traffic": None,
+        "traffic": traffic,
         "note": "compute-bound kernel: neither 'hbm' nor 'tensor' applies (SURVEY §8d). achieved = 12 FP32-pipe slots per "
                 "interaction counted as FMA (2 flop) x interactions per launch / CUDA-event launch duration; peak = "
                 f"148 SMs x 128 lanes x 2 x {max_mhz:.0f} MHz ({peak_src}; MEASURED_PEAKS.json has no FP32 entry), so "
