@@ -79,14 +79,16 @@ struct KernelVariant {
                     force_smem_bytes<THREADS, R, TJB, ST, WP>() }
 const KernelVariant g_variants[] = {
     // default first; chosen from the B200 sweep in profiles/ (tools/kbench)
-    VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3),
+    // 8 targets per thread and only 2 warps per scheduler: the operand-reuse cache keeps hitting while one warp keeps
+    // issuing, which is what gets the accumulate FFMA2 triples back to 2 cycles
     VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, false, 1, 2),
-    VARIANT("pk_t256_r4_tj4_st2_cta_u2_mb2", 256, 4, 4, 2, 1, false, 2, 2),
+    VARIANT("pk_t128_r8_tj4_st2_cta_u1_mb2", 128, 8, 4, 2, 1, false, 1, 2),
+    VARIANT("pk_t256_r8_tj2_st3_cta_u1_mb1", 256, 8, 2, 3, 1, false, 1, 1),
+    VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3),
     VARIANT("sc_t256_r4_tj2_st3_cta_u1_mb2", 256, 4, 2, 3, 0, false, 1, 2),
-    VARIANT("ps_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 2, false, 2, 3),
 };
 constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
-constexpr uint64_t SLICE_ALIGN = 1024; // multiple of THREADS*R of every variant and of BLK
+constexpr uint64_t SLICE_ALIGN = 2048; // multiple of THREADS*R of every variant and of BLK
 constexpr uint32_t MAX_ROWS = 64;
 constexpr int N_TIMER_SLOTS = 8;
 
@@ -152,25 +154,6 @@ int fail(b200nb_ctx *c, int code, const char *fmt, ...)
         if (r_ != ncclSuccess)                                                                                         \
             return fail(c, B200NB_ENCCL, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
-
-// chunks per slice k (S = k*P): maximise CTAs / (waves * slots) over the two launches of a step
-// (own-slice chunks [0,k) and remote chunks [k,S)); for P == 1 it is the single-launch plan.
-uint32_t plan_k(uint32_t n_itiles, uint32_t blocks_per_slice, uint32_t slots, int tjb, int n_ranks)
-{
-    if (n_ranks == 1) return plan_chunks(n_itiles, blocks_per_slice, slots, 2u * tjb, MAX_ROWS).n_chunks;
-    const uint32_t k_hi = std::max(1u, std::min(MAX_ROWS / (uint32_t)n_ranks, blocks_per_slice / (2u * tjb)));
-    uint32_t best = 1;
-    double best_score = -1;
-    for (uint32_t k = 1; k <= k_hi; ++k) {
-        const uint64_t ma = (uint64_t)n_itiles * k, mb = ma * (n_ranks - 1);
-        const uint64_t wa = (ma + slots - 1) / slots, wb = (mb + slots - 1) / slots;
-        const double eff = (double)(ma + mb) / (double)((wa + wb) * slots);
-        const double ragged = (double)blocks_per_slice / (double)(k * ((blocks_per_slice + k - 1) / k));
-        const double score = eff * ragged - 1e-4 * k;
-        if (score > best_score) { best_score = score; best = k; }
-    }
-    return best;
-}
 
 int alloc_shard(b200nb_ctx *c, Shard &s)
 {
@@ -258,7 +241,8 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     }
     const Shard &s0 = c->shards[0];
     const uint32_t ti = c->kv->threads * c->kv->r;
-    c->k_per_slice = plan_k((uint32_t)(c->L / ti), (uint32_t)(c->L / BLK), (uint32_t)(s0.n_sms * s0.occ), c->kv->tjb, n_ranks);
+    c->k_per_slice = plan_chunks((uint32_t)(c->L / ti), (uint32_t)(c->L / BLK), (uint32_t)(s0.n_sms * s0.occ),
+                                 (uint32_t)n_ranks, MAX_ROWS, (uint32_t)(4 * c->kv->tjb)).n_chunks;
     c->rows = c->k_per_slice * n_ranks;
     for (auto &s : c->shards)
         if (int rc = alloc_buffers(c, s)) return bail(rc);

@@ -155,6 +155,62 @@ __device__ __forceinline__ uint64_t acc_fma(uint64_t f, uint64_t d, uint64_t acc
     return pk2(fmaf(f0, d0, a0), fmaf(f1, d1, a1));
 }
 
+// Compile-time scheduling knobs.  They only permute independent statements (no numerical effect beyond the order
+// of three commutative FMA terms) but change how ptxas interleaves the chains, i.e. how many accumulate triples keep
+// the force factor in the operand-reuse cache; tools/tune_schedule.py scores every combination on the SASS with
+// the measured register-read model and the winners are confirmed on the GPU.
+#ifndef B200NB_KNOB_FMUL
+#define B200NB_KNOB_FMUL 0  // 0: (inv*inv)*(g*inv), 1: ((inv*inv)*inv)*g
+#endif
+#ifndef B200NB_KNOB_LOOP
+#define B200NB_KNOB_LOOP 0  // 0: source-pair outer / target inner, 1: target outer / source-pair inner
+#endif
+#ifndef B200NB_KNOB_DORD
+#define B200NB_KNOB_DORD 3  // permutation of (x,y,z) in the r^2 chain
+#endif
+#ifndef B200NB_KNOB_AORD
+#define B200NB_KNOB_AORD 1  // permutation of (x,y,z) in the accumulate triple
+#endif
+
+template <int P> struct Perm3;
+template <> struct Perm3<0> { static constexpr int a = 0, b = 1, c = 2; };
+template <> struct Perm3<1> { static constexpr int a = 0, b = 2, c = 1; };
+template <> struct Perm3<2> { static constexpr int a = 1, b = 0, c = 2; };
+template <> struct Perm3<3> { static constexpr int a = 1, b = 2, c = 0; };
+template <> struct Perm3<4> { static constexpr int a = 2, b = 0, c = 1; };
+template <> struct Perm3<5> { static constexpr int a = 2, b = 1, c = 0; };
+
+// one target against one packed source pair: 3 FADD2 + 3 FFMA2 + 2 MUFU.RSQ + 3 FMUL2 + 3 FFMA2
+template <bool SCALAR_ACC>
+__device__ __forceinline__ void pair_interaction(const uint64_t (&sj)[3], uint64_t gj, float xi, float yi, float zi,
+                                                 uint64_t soft2p, uint64_t (&acc)[3])
+{
+    uint64_t d3[3];
+    d3[0] = sub2(sj[0], pk2(xi, xi));
+    d3[1] = sub2(sj[1], pk2(yi, yi));
+    d3[2] = sub2(sj[2], pk2(zi, zi));
+    using D = Perm3<B200NB_KNOB_DORD>;
+    uint64_t d = fma2(d3[D::a], d3[D::a], soft2p);
+    d = fma2(d3[D::b], d3[D::b], d);
+    d = fma2(d3[D::c], d3[D::c], d);
+    float d0, d1;
+    upk2(d, d0, d1);
+    const uint64_t inv = pk2(rsqrt_approx(d0), rsqrt_approx(d1));
+#if B200NB_KNOB_FMUL == 0
+    const uint64_t gi = mul2(gj, inv);
+    const uint64_t i2 = mul2(inv, inv);
+    const uint64_t f = mul2(i2, gi);
+#else
+    const uint64_t i2 = mul2(inv, inv);
+    const uint64_t i3 = mul2(i2, inv);
+    const uint64_t f = mul2(i3, gj);
+#endif
+    using A = Perm3<B200NB_KNOB_AORD>;
+    acc[A::a] = acc_fma<SCALAR_ACC>(f, d3[A::a], acc[A::a]);
+    acc[A::b] = acc_fma<SCALAR_ACC>(f, d3[A::b], acc[A::b]);
+    acc[A::c] = acc_fma<SCALAR_ACC>(f, d3[A::c], acc[A::c]);
+}
+
 // One AoSoA block (128 sources) against R register-blocked targets, packed f32x2 along the sources.
 template <int R, int U, bool SCALAR_ACC>
 __device__ __forceinline__ void block_packed(const float *__restrict__ sb, const float (&xi)[R], const float (&yi)[R],
@@ -167,29 +223,23 @@ __device__ __forceinline__ void block_packed(const float *__restrict__ sb, const
         const float4 yv = *reinterpret_cast<const float4 *>(sb + BLK + j);
         const float4 zv = *reinterpret_cast<const float4 *>(sb + 2 * BLK + j);
         const float4 gv = *reinterpret_cast<const float4 *>(sb + 3 * BLK + j);
+        const uint64_t s0[3] = {pk2(xv.x, xv.y), pk2(yv.x, yv.y), pk2(zv.x, zv.y)};
+        const uint64_t s1[3] = {pk2(xv.z, xv.w), pk2(yv.z, yv.w), pk2(zv.z, zv.w)};
+        const uint64_t g0 = pk2(gv.x, gv.y), g1 = pk2(gv.z, gv.w);
+#if B200NB_KNOB_LOOP == 0
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const uint64_t xj = h ? pk2(xv.z, xv.w) : pk2(xv.x, xv.y);
-            const uint64_t yj = h ? pk2(yv.z, yv.w) : pk2(yv.x, yv.y);
-            const uint64_t zj = h ? pk2(zv.z, zv.w) : pk2(zv.x, zv.y);
-            const uint64_t gj = h ? pk2(gv.z, gv.w) : pk2(gv.x, gv.y);
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                const uint64_t dx = sub2(xj, pk2(xi[k], xi[k]));
-                const uint64_t dy = sub2(yj, pk2(yi[k], yi[k]));
-                const uint64_t dz = sub2(zj, pk2(zi[k], zi[k]));
-                uint64_t d = fma2(dx, dx, soft2p);
-                d = fma2(dy, dy, d);
-                d = fma2(dz, dz, d);
-                float d0, d1;
-                upk2(d, d0, d1);
-                const uint64_t inv = pk2(rsqrt_approx(d0), rsqrt_approx(d1));
-                const uint64_t gi = mul2(gj, inv);
-                const uint64_t i2 = mul2(inv, inv);
-                const uint64_t f = mul2(i2, gi);
-                ax[k] = acc_fma<SCALAR_ACC>(f, dx, ax[k]);
-                ay[k] = acc_fma<SCALAR_ACC>(f, dy, ay[k]);
-                az[k] = acc_fma<SCALAR_ACC>(f, dz, az[k]);
+#else
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#endif
+                uint64_t acc[3] = {ax[k], ay[k], az[k]};
+                pair_interaction<SCALAR_ACC>(h ? s1 : s0, h ? g1 : g0, xi[k], yi[k], zi[k], soft2p, acc);
+                ax[k] = acc[0]; ay[k] = acc[1]; az[k] = acc[2];
             }
         }
     }

@@ -1,7 +1,7 @@
 // Host-side launch planning for the 2-D (target tiles x source chunks) force grid.
 // The reference sizes its grid as ceil(N/1024) CTAs (SimulationNBodyCUDATileFullDevice.cu:181), which leaves
-// 100 of 148 SMs half-loaded at N=200k; here the number of source chunks is chosen so that the CTA count is
-// as close as possible to a whole number of waves over (SM count x resident CTAs per SM).
+// 100 of 148 SMs half-loaded at N=200k; here the source axis is cut into chunks so that the CTA count is many whole
+// waves over (SM count x resident CTAs per SM), independently of N.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -9,31 +9,34 @@
 namespace b200nb {
 
 struct ChunkPlan {
-    uint32_t n_chunks;
-    double wave_efficiency; // CTAs / (waves * slots)
-    uint32_t waves;
+    uint32_t n_chunks;       // chunks per slice (k); the grid has k * n_ranks chunks in total
+    uint32_t waves;          // CTA waves of one force pass (both launches when n_ranks > 1)
+    double wave_efficiency;  // CTAs / (waves * slots)
 };
 
-// n_itiles: target tiles; n_src_blocks: AoSoA source blocks; slots: SMs * resident CTAs/SM;
-// min_blocks_per_chunk: keep the TMA pipeline busy; max_chunks: bounds the partial-sum buffer.
-inline ChunkPlan plan_chunks(uint32_t n_itiles, uint32_t n_src_blocks, uint32_t slots, uint32_t min_blocks_per_chunk,
-                             uint32_t max_chunks)
+// Cost model fitted to the B200 chunk sweep (profiles/): one pass takes (waves + 1/2) CTA-times — the CTA scheduler
+// refills SMs dynamically, so only about half a CTA of tail is lost — and a CTA costs its blocks plus ~0.3 block of
+// prologue/epilogue (pipeline fill, target loads, partial stores).  Many short CTAs (>= ~40 waves) win until the
+// per-CTA overhead catches up.
+//   n_itiles          target tiles of one rank
+//   blocks_per_slice  128-body source blocks in one rank's slice
+//   slots             SMs x resident CTAs per SM
+//   n_ranks           the own-slice chunks [0,k) and the remote chunks [k, k*n_ranks) are separate launches
+inline ChunkPlan plan_chunks(uint32_t n_itiles, uint32_t blocks_per_slice, uint32_t slots, uint32_t n_ranks,
+                             uint32_t max_rows, uint32_t min_blocks_per_chunk = 8)
 {
-    ChunkPlan best{1, 0.0, 1};
-    const uint32_t s_hi = std::max(1u, std::min(max_chunks, n_src_blocks / std::max(1u, min_blocks_per_chunk)));
-    double best_score = -1.0;
-    for (uint32_t s = 1; s <= s_hi; ++s) {
-        const uint64_t m = (uint64_t)n_itiles * s;
-        const uint64_t waves = (m + slots - 1) / slots;
-        const double eff = (double)m / (double)(waves * slots);
-        // chunk sizes differ by at most one block: account for the longest chunk
-        const double ragged = (double)n_src_blocks / (double)(s * ((n_src_blocks + s - 1) / s));
-        // prefer >= 4 waves (dynamic CTA scheduling evens out SM speed differences), then fewer chunks
-        const double wave_bonus = waves >= 4 ? 0.0 : -0.02 * (double)(4 - waves);
-        const double score = eff * ragged + wave_bonus - 1e-4 * s;
-        if (score > best_score) {
-            best_score = score;
-            best = ChunkPlan{s, eff * ragged, (uint32_t)waves};
+    const uint32_t k_hi = std::max(1u, std::min(max_rows / std::max(1u, n_ranks), blocks_per_slice / std::max(1u, min_blocks_per_chunk)));
+    ChunkPlan best{1, 1, 0.0};
+    double best_t = 1e300;
+    for (uint32_t k = 1; k <= k_hi; ++k) {
+        const uint64_t m_own = (uint64_t)n_itiles * k, m_rem = m_own * (n_ranks - 1);
+        const uint64_t w_own = (m_own + slots - 1) / slots, w_rem = (m_rem + slots - 1) / slots;
+        const double bpc = (double)blocks_per_slice / k;
+        const double tails = n_ranks > 1 ? 1.0 : 0.5; // two launches, two tails
+        const double t = ((double)(w_own + w_rem) + tails) * (bpc + 0.3);
+        if (t < best_t) {
+            best_t = t;
+            best = ChunkPlan{k, (uint32_t)(w_own + w_rem), (double)(m_own + m_rem) / (double)((w_own + w_rem) * slots)};
         }
     }
     return best;

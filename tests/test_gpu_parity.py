@@ -206,7 +206,8 @@ def test_state_errors(b200, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", ["pk_t128_r8_tj2_st3_cta_u1_mb2", "pk_t256_r4_tj4_st2_cta_u2_mb2", "sc_t256_r4_tj2_st3_cta_u1_mb2"])
+@pytest.mark.parametrize("variant", ["pk_t128_r8_tj4_st2_cta_u1_mb2", "pk_t256_r8_tj2_st3_cta_u1_mb1", "pk_t256_r2_tj2_st3_cta_u2_mb3",
+                                     "sc_t256_r4_tj2_st3_cta_u1_mb2"])
 def test_other_kernel_variants(b200, oracle, variant, monkeypatch):
     monkeypatch.setenv("B200NB_VARIANT", variant)
     d = oracle.init_bodies("random", 5000)

@@ -188,27 +188,26 @@ static void register_all()
 {
     //            THR  R TJB ST MATH  WP    U MINB      MATH: 0 scalar, 1 packed, 2 packed + scalar accumulate
     reg_variant<256, 2, 2, 3, 1, false, 2, 3>();
-    reg_variant<256, 2, 2, 3, 2, false, 2, 3>();
-    reg_variant<256, 2, 2, 3, 2, false, 1, 3>();
-    reg_variant<256, 2, 2, 3, 2, false, 4, 3>();
-    reg_variant<256, 2, 2, 3, 2, false, 2, 2>();
-    reg_variant<256, 2, 2, 3, 2, false, 2, 4>();
-    reg_variant<256, 1, 2, 3, 2, false, 2, 4>();
-    reg_variant<256, 1, 2, 3, 2, false, 4, 6>();
-    reg_variant<256, 3, 2, 3, 2, false, 2, 2>();
-    reg_variant<256, 4, 2, 3, 2, false, 2, 2>();
-    reg_variant<256, 4, 2, 3, 2, false, 1, 2>();
     reg_variant<256, 4, 2, 3, 1, false, 2, 2>();
-    reg_variant<128, 4, 2, 3, 2, false, 2, 3>();
-    reg_variant<128, 4, 2, 3, 2, false, 2, 4>();
-    reg_variant<128, 8, 2, 3, 2, false, 1, 2>();
     reg_variant<128, 8, 2, 3, 1, false, 1, 2>();
-    reg_variant<256, 8, 2, 3, 2, false, 1, 1>();
-    reg_variant<128, 6, 2, 3, 2, false, 1, 2>();
-    reg_variant<512, 2, 2, 3, 2, false, 2, 1>();
-    reg_variant<256, 2, 1, 3, 2, true, 2, 3>();
-    reg_variant<256, 2, 4, 2, 2, false, 2, 3>();
-    reg_variant<256, 2, 1, 4, 2, false, 2, 3>();
+    // few warps, high per-thread ILP: the operand-reuse cache only hits while one warp keeps issuing
+    reg_variant<128, 8, 2, 3, 1, false, 1, 1>();
+    reg_variant<128, 8, 2, 3, 1, false, 2, 2>();
+    reg_variant<128, 8, 4, 2, 1, false, 1, 2>();
+    reg_variant<128, 8, 1, 4, 1, false, 1, 2>();
+    reg_variant<128, 8, 2, 2, 1, false, 1, 2>();
+    reg_variant<64, 8, 2, 3, 1, false, 1, 4>();
+    reg_variant<64, 16, 2, 3, 1, false, 1, 2>();
+    reg_variant<128, 6, 2, 3, 1, false, 1, 2>();
+    reg_variant<128, 6, 2, 3, 1, false, 1, 3>();
+    reg_variant<128, 10, 2, 3, 1, false, 1, 2>();
+    reg_variant<128, 12, 2, 3, 1, false, 1, 2>();
+    reg_variant<128, 12, 2, 3, 1, false, 1, 1>();
+    reg_variant<256, 8, 2, 3, 1, false, 1, 1>();
+    reg_variant<256, 6, 2, 3, 1, false, 1, 1>();
+    reg_variant<128, 4, 2, 3, 1, false, 2, 3>();
+    reg_variant<128, 4, 2, 3, 1, false, 1, 4>();
+    reg_variant<128, 8, 1, 3, 1, true, 1, 2>();
     // scalar FP32 comparator (13 issue slots / interaction)
     reg_variant<256, 4, 2, 3, 0, false, 1, 2>();
 }
@@ -217,7 +216,7 @@ static void make_problem(Problem &p, size_t n, int sms)
 {
     p.n = n;
     p.sms = sms;
-    const size_t align = 8192; // multiple of every THREADS*R used above
+    const size_t align = 30720; // lcm of every THREADS*R registered below // multiple of every THREADS*R used above
     p.n_pad = (n + align - 1) / align * align;
     p.soft2 = 2e8f * 2e8f;
     p.hx.resize(p.n_pad); p.hy.resize(p.n_pad); p.hz.resize(p.n_pad); p.hg.resize(p.n_pad);
@@ -336,7 +335,7 @@ int main(int argc, char **argv)
         const uint32_t ti = v.threads * v.r;
         const uint32_t n_itiles = (uint32_t)(p.n_pad / ti);
         const uint32_t n_blocks = (uint32_t)(p.n_pad / BLK);
-        ChunkPlan plan = plan_chunks(n_itiles, n_blocks, (uint32_t)(sms * occ), (uint32_t)(2 * v.tjb), (uint32_t)p.partial_rows);
+        ChunkPlan plan = plan_chunks(n_itiles, n_blocks, (uint32_t)(sms * occ), 1u, (uint32_t)p.partial_rows, (uint32_t)(4 * v.tjb));
         if (chunks_override > 0) plan.n_chunks = chunks_override;
         ForceArgs a{};
         a.src = p.d_bodies; a.tgt = p.d_bodies; a.partial = p.d_partial;
