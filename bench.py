@@ -203,7 +203,24 @@ def run_reference_arm(args, rank):
     }), flush=True)
 
 
+class StdoutToStderr:
+    """NCCL (and anything else native) may print to fd 1; the contract is ONE JSON line on stdout.  Everything written
+    to fd 1 while this is active goes to stderr; emit() writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
 def run_b200_arm(args, rank, world, local_rank):
+    out_guard = StdoutToStderr()
     import torch
     import b200nb
 
@@ -283,6 +300,9 @@ def run_b200_arm(args, rank, world, local_rank):
 
     if rank != 0:
         ctx.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (the force pass): FP32 pipe, not HBM, not tensor
@@ -336,8 +356,11 @@ def run_b200_arm(args, rank, world, local_rank):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out), flush=True)
+    out_guard.emit(json.dumps(out))
     ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
