@@ -100,6 +100,16 @@ def _cpu_flags():
     return set()
 
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def load_reference():
     """Best ISA build of the reference CPU path present in oracle/_ref (built from /root/reference by oracle/build_ref.sh)."""
     flags = _cpu_flags()
@@ -146,9 +156,21 @@ def cpu_reference_rate(scheme, n_sample, budget_s, tag="cpu+omp"):
     iters = int(max(2, min(200, budget_s * 1e3 / max(ms1, 1e-3))))
     ms = L.ref_run(tag.encode(), n_sample, scheme.encode(), SOFT, DT, iters, *none)
     rate = float(n_sample) ** 2 * iters / (ms * 1e-3) / 1e9
-    return {"value": rate, "unit": "G-int/s", "cores": cores if tag == "cpu+omp" else 1, "kind": "reference",
-            "sample": f"reference {tag} ({desc}), {iters} iterations of murb -n {n_sample} -s {scheme} (full force pass + integrator), "
-                      f"{ms / iters:.2f} ms/iter", "ms_per_iter": ms / iters, "iters": iters, "n_sample": n_sample}
+    out = {"value": rate, "unit": "G-int/s", "cores": cores if tag == "cpu+omp" else 1, "kind": "reference",
+           "sample": f"reference {tag} ({desc}), {iters} iterations of murb -n {n_sample} -s {scheme} (full force pass + integrator), "
+                     f"{ms / iters:.2f} ms/iter", "ms_per_iter": ms / iters, "iters": iters, "n_sample": n_sample,
+           "cpu_model": _cpu_model()}
+    if tag == "cpu+omp":
+        # the other reference CPU paths the north star asks for, single thread, same ICs (bounded: a few seconds each)
+        others = {}
+        for t, it in (("cpu+simd", 3), ("cpu+naive", 1)):
+            n_t = n_sample if t == "cpu+simd" else 8000   # cpu+naive at 30000 is ~8 s/iteration; 8000 is the Report's own size
+            L.ref_run(t.encode(), n_t, scheme.encode(), SOFT, DT, 1 if t == "cpu+simd" else 0, *none)
+            ms_t = L.ref_run(t.encode(), n_t, scheme.encode(), SOFT, DT, it, *none)
+            others[t] = {"value": float(n_t) ** 2 * it / (ms_t * 1e-3) / 1e9, "unit": "G-int/s", "cores": 1, "n_sample": n_t,
+                         "iters": it, "ms_per_iter": ms_t / it}
+        out["other_reference_paths"] = others
+    return out
 
 
 def oracle_port_rate(scheme, budget_s):

@@ -3,6 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <limits>
 
 #include "b200nb.h"
 
@@ -132,6 +135,27 @@ SimulationNBodyB200::SimulationNBodyB200(const BodiesAllocatorInterface<float> &
     this->nGpus = envInt("MURB_B200_NGPUS", 1);
     this->b200Bodies->bind(this->G, this->soft, this->nGpus);
     this->allocatedBytes = this->bodies->getAllocatedBytes();
+    const char *csv = std::getenv("MURB_B200_METRICS_CSV");
+    if (csv && *csv) this->metricsPath = csv;
+}
+
+SimulationNBodyB200::~SimulationNBodyB200()
+{
+    if (!this->metricsPath.empty()) this->saveMetricsToCSV(this->metricsPath);
+}
+
+void SimulationNBodyB200::saveMetricsToCSV(const std::string &filePath) const
+{
+    // same columns as SimulationHistory<T>::saveMetricsToCSV; angular momentum and density centre are declared but
+    // never computed upstream (they stay 0 there too)
+    std::ofstream out(filePath);
+    if (!out.is_open()) {
+        std::fprintf(stderr, "gpu+b200: cannot open metrics file '%s'\n", filePath.c_str());
+        return;
+    }
+    out << "iteration,energy,ang_momentum,density_center_x,density_center_y,density_center_z\n";
+    out << std::setprecision(std::numeric_limits<double>::max_digits10);
+    for (size_t i = 0; i < this->energies.size(); i++) out << i << ',' << this->energies[i] << ",0,0,0,0\n";
 }
 
 void SimulationNBodyB200::computeOneIteration()
@@ -141,6 +165,7 @@ void SimulationNBodyB200::computeOneIteration()
     // main.cpp:353-371 joins the current device only; with several GPUs the others are joined here
     if (b200nb_n_local_gpus(c) > 1) check(b200nb_sync(c), c, "b200nb_sync");
     this->b200Bodies->invalidateDataSoA();
+    if (!this->metricsPath.empty()) this->energies.push_back(this->computeEnergy());
 }
 
 void SimulationNBodyB200::computeAccelerationsOnly()

@@ -10,6 +10,9 @@
 // Environment (precedent: MURB_HETERO_GPU_FRACTION / MURB_HETERO_MIN_N, SimulationNBodyHetero.cu:217-227):
 //   MURB_B200_NGPUS       number of GPUs to shard the targets over (default 1; 0 = all visible)
 //   MURB_B200_INTEGRATOR  "murb" (default) or "leapfrog"; the tag gpu+b200+leapfrog selects leapfrog too
+//   MURB_B200_METRICS_CSV path: track the total energy after every iteration (what gpu+tracking does,
+//                         SimulationNBodyCUDAPropertyTracking.cu:217-369) and write it on destruction in the format of
+//                         SimulationHistory::saveMetricsToCSV (src/common/core/SimulationHistory.cpp:103-122)
 #ifndef SIMULATION_N_BODY_B200_HPP_
 #define SIMULATION_N_BODY_B200_HPP_
 
@@ -65,16 +68,20 @@ class SimulationNBodyB200 : public SimulationNBodyInterface<float> {
     int integrator; // B200NB_INTEGRATOR_*
     int nGpus;
     accSoA_t<float> accSoA;
+    std::string metricsPath;       // empty: no tracking
+    std::vector<double> energies;  // energies[i] = total energy after iteration i (fp64, like GPUSimulationHistory<double>)
 
   public:
     SimulationNBodyB200(const BodiesAllocatorInterface<float> &allocator, const float soft = 0.035f,
                         const bool leapfrog = false);
-    virtual ~SimulationNBodyB200() = default;
+    virtual ~SimulationNBodyB200();
     virtual void computeOneIteration();
     const accSoA_t<float> &getAccSoA(); // accelerations of the last force pass (…PropertyTracking.cu:308-319)
     void computeAccelerationsOnly();    // force pass without integration (accuracy tests)
     double computeEnergy();             // fp64 total energy (…PropertyTracking.cu:217-304 definition)
     const char *kernelName() const;
+    const std::vector<double> &getEnergies() const { return energies; }
+    void saveMetricsToCSV(const std::string &filePath) const;
 };
 
 #endif /* SIMULATION_N_BODY_B200_HPP_ */

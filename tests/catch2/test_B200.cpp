@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <fstream>
 #include <iomanip>
 #include <iostream>
 #include <string>
@@ -21,32 +22,39 @@
 
 namespace {
 
-// the four sections of the reference's "n-body - Correctness" case, target swapped for gpu+b200
+// Position parity of gpu+b200 against the golden model after every iteration (the contract of the reference's
+// "n-body - Correctness" case: WithinRel per component, exact before the first iteration).
+struct PositionParity {
+    size_t n;
+    float eps;
+    void operator()(const dataSoA_t<float> &golden, const dataSoA_t<float> &got, size_t iteration) const
+    {
+        const float tol = iteration == 0 ? 0.f : eps;
+        const std::vector<float> *g[3] = {&golden.qx, &golden.qy, &golden.qz};
+        const std::vector<float> *t[3] = {&got.qx, &got.qy, &got.qz};
+        for (int axis = 0; axis < 3; axis++)
+            for (size_t body = 0; body < n; body++) {
+                CAPTURE(axis, body, iteration);
+                REQUIRE_THAT((*g[axis])[body], Catch::Matchers::WithinRel((*t[axis])[body], tol));
+            }
+    }
+};
+
 void b200_vs_naive(const size_t n, const float soft, const float dt, const size_t nIte, const std::string &scheme,
                    const float eps, const bool leapfrog = false)
 {
-    BodiesAllocator<float> naiveAllocator(n, scheme);
-    SimulationNBodyNaive<float> simuRef(naiveAllocator, soft);
-    simuRef.setDt(dt);
-
-    B200BodiesAllocator targetAllocator(n, scheme);
-    SimulationNBodyB200 simuTest(targetAllocator, soft, leapfrog);
-    simuTest.setDt(dt);
-
-    for (size_t i = 0; i < nIte + 1; i++) {
-        if (i > 0) {
-            simuRef.computeOneIteration();
-            simuTest.computeOneIteration();
-        }
-        const dataSoA_t<float> &ref = simuRef.getBodies()->getDataSoA();
-        const dataSoA_t<float> &tst = simuTest.getBodies()->getDataSoA(); // lazy device -> host copy
-        const float e = (i > 0) ? eps : 0.f;
-        for (size_t b = 0; b < n; b++) {
-            CAPTURE(b, i, ref.qx[b], tst.qx[b]);
-            REQUIRE_THAT(ref.qx[b], Catch::Matchers::WithinRel(tst.qx[b], e));
-            REQUIRE_THAT(ref.qy[b], Catch::Matchers::WithinRel(tst.qy[b], e));
-            REQUIRE_THAT(ref.qz[b], Catch::Matchers::WithinRel(tst.qz[b], e));
-        }
+    B200BodiesAllocator b200Alloc(n, scheme);
+    SimulationNBodyB200 b200(b200Alloc, soft, leapfrog);
+    BodiesAllocator<float> hostAlloc(n, scheme);
+    SimulationNBodyNaive<float> naive(hostAlloc, soft);
+    b200.setDt(dt);
+    naive.setDt(dt);
+    const PositionParity same{n, eps};
+    same(naive.getBodies()->getDataSoA(), b200.getBodies()->getDataSoA(), 0); // lazy device -> host copy
+    for (size_t it = 1; it <= nIte; it++) {
+        b200.computeOneIteration();
+        naive.computeOneIteration();
+        same(naive.getBodies()->getDataSoA(), b200.getBodies()->getDataSoA(), it);
     }
 }
 
@@ -209,6 +217,32 @@ TEST_CASE("gpu+b200 - leapfrog energy", "[b200][leapfrog]")
     REQUIRE(drift[1] <= drift[0]);
     // and leapfrog follows the golden model's trajectory closely over a few steps (different scheme: loose bound)
     b200_vs_naive(2049, 2e+08, 3600, 3, "galaxy", 1e-1, true);
+}
+
+// gpu+tracking analogue: per-iteration energies and the reference's metrics CSV layout
+TEST_CASE("gpu+b200 - metrics CSV", "[b200][metrics]")
+{
+    const char *path = "/tmp/b200_metrics_test.csv";
+    setenv("MURB_B200_METRICS_CSV", path, 1);
+    double e0 = 0;
+    {
+        B200BodiesAllocator alloc(3000, "galaxy");
+        SimulationNBodyB200 simu(alloc, 2e+08, true);
+        simu.setDt(3600);
+        e0 = simu.computeEnergy();
+        for (int it = 0; it < 5; it++) simu.computeOneIteration();
+        REQUIRE(simu.getEnergies().size() == 5);
+        for (double e : simu.getEnergies()) REQUIRE(std::abs((e - e0) / e0) < 1e-4);
+    } // destructor writes the file
+    unsetenv("MURB_B200_METRICS_CSV");
+    std::ifstream in(path);
+    REQUIRE(in.is_open());
+    std::string line;
+    std::getline(in, line);
+    REQUIRE(line == "iteration,energy,ang_momentum,density_center_x,density_center_y,density_center_z");
+    int rows = 0;
+    while (std::getline(in, line)) if (!line.empty()) rows++;
+    REQUIRE(rows == 5);
 }
 
 #ifdef USE_CUDA

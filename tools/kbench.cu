@@ -166,17 +166,18 @@ struct Variant {
 
 static std::vector<Variant> g_variants;
 
-template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MINB> static void reg_variant()
+template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MINB> static void reg_variant(size_t pad_smem = 0)
 {
     Variant v;
     char nm[128];
     snprintf(nm, sizeof nm, "%s_t%d_r%d_tj%d_st%d_%s_u%d_mb%d", MATH == 0 ? "sc" : (MATH == 1 ? "pk" : "ps"), THREADS, R, TJB, ST,
              WP ? "warp" : "cta", U, MINB);
     v.name = nm;
+    if (pad_smem) v.name += "_pad" + std::to_string(pad_smem / 1024) + "k";
     v.threads = THREADS; v.r = R; v.tjb = TJB; v.st = ST; v.packed = MATH; v.warp_private = WP; v.u = U; v.minb = MINB;
     auto k = force_kernel<THREADS, R, TJB, ST, MATH, WP, U, MINB>;
     v.fn = (const void *)k;
-    v.smem = force_smem_bytes<THREADS, R, TJB, ST, WP>();
+    v.smem = force_smem_bytes<THREADS, R, TJB, ST, WP>() + pad_smem; // padding only lowers the occupancy
     v.launch = [k, smem = v.smem](const ForceArgs &a, dim3 grid) {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, THREADS, smem>>>(a);
@@ -192,6 +193,12 @@ static void register_all()
     reg_variant<128, 8, 2, 3, 1, false, 1, 2>();
     // few warps, high per-thread ILP: the operand-reuse cache only hits while one warp keeps issuing
     reg_variant<128, 8, 2, 3, 1, false, 1, 1>();
+    reg_variant<128, 8, 2, 3, 1, false, 1, 1>(120 * 1024);  // 1 CTA/SM = 1 warp per scheduler
+    reg_variant<64, 8, 2, 3, 1, false, 1, 4>(60 * 1024);    // 3 CTAs of 2 warps
+    reg_variant<64, 8, 2, 3, 1, false, 1, 4>(100 * 1024);   // 2 CTAs of 2 warps = 1 warp per scheduler
+    reg_variant<128, 8, 2, 3, 1, false, 2, 1>(120 * 1024);
+    reg_variant<96, 8, 2, 3, 1, false, 1, 2>();              // 3 warps per CTA, 2 CTAs: 1.5 warps per scheduler
+    reg_variant<192, 8, 2, 3, 1, false, 1, 1>();             // 6 warps/SM
     reg_variant<128, 8, 2, 3, 1, false, 2, 2>();
     reg_variant<128, 8, 4, 2, 1, false, 1, 2>();
     reg_variant<128, 8, 1, 4, 1, false, 1, 2>();
