@@ -47,6 +47,7 @@ class ClockSampler:
                0x100: "display_clock_setting"}
 
     def __init__(self, index):
+        self.index = index
         self.samples, self.reasons, self.power = [], set(), []
         self._stop = threading.Event()
         self._thread = None
@@ -75,10 +76,29 @@ class ClockSampler:
                 pass
             self._stop.wait(0.05)
 
+    def _run_smi(self):
+        # fallback without NVML bindings: the recipe's nvidia-smi line (B200_PROFILING.md), polled
+        import subprocess
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(int(float(out[0])))
+                self.max_mhz = int(float(out[1]))
+                self.power.append(float(out[2]))
+                for nm, v in zip(names, out[3:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
     def start(self):
-        if self.nv:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
+        self._thread = threading.Thread(target=self._run if self.nv else self._run_smi, daemon=True)
+        self._thread.start()
 
     def stop(self):
         self._stop.set()

@@ -139,6 +139,13 @@ int b200nb_host_free(void *ptr);
 int b200nb_init_bodies(int scheme, uint64_t n, unsigned seed, float *qx, float *qy, float *qz, float *vx, float *vy,
                        float *vz, float *m, float *r);
 
+/* The reference's file-based scheme, Bodies<T>::initMilkyWayAndromeda (src/common/core/Bodies.cpp:82-153): a text file
+ * with one body per non-empty line, "mass x y z vx vy vz" in galaxy units, rescaled per galaxy component.  Count the
+ * bodies first, then load into arrays of that many floats.  Host only. */
+int b200nb_tab_count(const char *path, uint64_t *n_bodies);
+int b200nb_tab_load(const char *path, uint64_t n, float *qx, float *qy, float *qz, float *vx, float *vy, float *vz,
+                    float *m, float *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ import numpy as np
 
 __all__ = [
     "B200Error", "Context", "SimulationNBodyB200", "B200Bodies", "init_bodies", "lib", "lib_path", "header_functions",
-    "G_F32", "INTEGRATOR_MURB", "INTEGRATOR_LEAPFROG", "slice_length",
+    "G_F32", "INTEGRATOR_MURB", "INTEGRATOR_LEAPFROG", "slice_length", "load_tab",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
         "b200nb_host_free": (c_int, [c_void_p]),
         "b200nb_init_bodies": (c_int, [c_int, c_uint64, c_uint] + [_FP] * 8),
         "b200nb_slice_length": (c_uint64, [c_uint64, c_int]),
+        "b200nb_tab_count": (c_int, [c_char_p, POINTER(c_uint64)]),
+        "b200nb_tab_load": (c_int, [c_char_p, c_uint64] + [_FP] * 8),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -115,6 +117,18 @@ def init_bodies(scheme: str, n: int, seed: int = 0) -> dict[str, np.ndarray]:
     rc = lib().b200nb_init_bodies(_SCHEMES[scheme], n, seed, *[_p(out[k]) for k in ("qx", "qy", "qz", "vx", "vy", "vz", "m", "r")])
     if rc != OK:
         raise B200Error(rc, "b200nb_init_bodies", "bad arguments")
+    return out
+
+
+def load_tab(path: str) -> dict[str, np.ndarray]:
+    """Bodies<float>::initMilkyWayAndromeda (Bodies.cpp:82-153): the reference's `.tab` initial-condition file."""
+    n = c_uint64()
+    if lib().b200nb_tab_count(path.encode(), byref(n)) != OK:
+        raise B200Error(EINVAL, "b200nb_tab_count", f"cannot read {path}")
+    out = {k: np.empty(n.value, dtype=np.float32) for k in ("qx", "qy", "qz", "vx", "vy", "vz", "m", "r")}
+    rc = lib().b200nb_tab_load(path.encode(), n.value, *[_p(out[k]) for k in ("qx", "qy", "qz", "vx", "vy", "vz", "m", "r")])
+    if rc != OK:
+        raise B200Error(rc, "b200nb_tab_load", f"parse error in {path}")
     return out
 
 

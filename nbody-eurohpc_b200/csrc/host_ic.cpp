@@ -11,6 +11,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <fstream>
+#include <sstream>
+#include <string>
 
 #include "../../include/b200nb.h"
 
@@ -97,4 +100,51 @@ extern "C" int b200nb_init_bodies(int scheme, uint64_t n, unsigned seed, float *
     else if (scheme == 1) random_box(n, seed, o);
     else return B200NB_EINVAL;
     return B200NB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- .tab loader
+// Bodies<float>::initMilkyWayAndromeda (src/common/core/Bodies.cpp:82-153): one body per non-empty line,
+// "mass x y z vx vy vz" in galaxy units, rescaled per component: the disk (16384), bulge (8192) and halo (16384)
+// bodies of the Milky Way come first inside each component pair and use (4.5e10, 4.0, 220), Andromeda's use
+// (9.4e10, 6.0, 260); radius is 1e5 for every body.  Values are parsed as float with operator>>, like the reference.
+extern "C" int b200nb_tab_count(const char *path, uint64_t *n_bodies)
+{
+    if (!path || !n_bodies) return B200NB_EINVAL;
+    std::ifstream file(path);
+    if (!file.is_open()) return B200NB_EINVAL;
+    uint64_t n = 0;
+    std::string line;
+    while (std::getline(file, line))
+        if (!line.empty()) ++n;
+    *n_bodies = n;
+    return B200NB_OK;
+}
+
+extern "C" int b200nb_tab_load(const char *path, uint64_t n, float *qx, float *qy, float *qz, float *vx, float *vy,
+                               float *vz, float *m, float *r)
+{
+    if (!path) return B200NB_EINVAL;
+    std::ifstream file(path);
+    if (!file.is_open()) return B200NB_EINVAL;
+    const BodyOut o{qx, qy, qz, vx, vy, vz, m, r};
+    const uint64_t disk = 16384, bulge = 8192, halo = 16384;
+    uint64_t i = 0;
+    std::string line;
+    while (i < n && std::getline(file, line)) {
+        if (line.empty()) continue;
+        std::istringstream iss(line);
+        float mi, x, y, z, u, v, w;
+        iss >> mi >> x >> y >> z >> u >> v >> w;
+        if (iss.fail()) return B200NB_EINVAL;
+        const bool milky_way = i < disk || (i >= 2 * disk && i < 2 * disk + bulge) ||
+                               (i >= 2 * (disk + bulge) && i < 2 * (disk + bulge) + halo);
+        const double sm = milky_way ? 4.5e10 : 9.4e10, sq = milky_way ? 4.0 : 6.0;
+        const int sv = milky_way ? 220 : 260;
+        mi = (float)((double)mi * sm);
+        x = (float)((double)x * sq); y = (float)((double)y * sq); z = (float)((double)z * sq);
+        u = u * (float)sv; v = v * (float)sv; w = w * (float)sv;
+        o.set(i, mi, 1e5f, x, y, z, u, v, w);
+        ++i;
+    }
+    return i == n ? B200NB_OK : B200NB_EINVAL;
 }

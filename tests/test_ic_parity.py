@@ -49,3 +49,43 @@ def test_live_reference(b200, oracle, scheme, n):
     for k in KEYS:
         assert np.array_equal(r[k].view(np.uint32), p[k].view(np.uint32)), k
         assert np.array_equal(r[k].view(np.uint32), o[k].view(np.uint32)), k
+
+
+def _write_tab(path, n, seed=3):
+    rng = np.random.default_rng(seed)
+    rows = rng.normal(size=(n, 7)) * np.array([1e-5, 3.0, 3.0, 0.5, 0.7, 0.7, 0.2]) + np.array([2e-5, 0, 0, 0, 0, 0, 0])
+    with open(path, "w") as f:
+        for k, r in enumerate(rows):
+            f.write(" ".join(f"{v:.7e}" for v in r) + "\n")
+            if k % 1000 == 7:
+                f.write("\n")  # empty lines are skipped by the reference
+
+
+def test_tab_loader_components(b200, tmp_path):
+    """initMilkyWayAndromeda (Bodies.cpp:82-153): component-dependent rescaling and the 1e5 radius."""
+    n = 83000  # crosses every component boundary: 16384 / 32768 / 40960 / 49152 / 65536 / 81920
+    path = str(tmp_path / "milkyway_andromeda.tab")
+    _write_tab(path, n)
+    d = b200.load_tab(path)
+    raw = np.array([[float(x) for x in l.split()] for l in open(path) if l.strip()], dtype=np.float32)
+    assert len(d["m"]) == n and np.all(d["r"] == np.float32(1e5))
+    for i, mw in ((0, True), (16383, True), (16384, False), (32768, True), (40959, True), (40960, False), (49152, True),
+                  (65535, True), (65536, False), (82999, False)):
+        sm, sq, sv = (4.5e10, 4.0, 220) if mw else (9.4e10, 6.0, 260)
+        assert d["m"][i] == np.float32(float(raw[i, 0]) * sm)
+        assert d["qx"][i] == np.float32(float(raw[i, 1]) * sq)
+        assert d["vz"][i] == np.float32(raw[i, 6] * np.float32(sv))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REPO, "oracle", "_ref", "libmurbref.so")), reason="reference not built here")
+def test_tab_loader_matches_live_reference(b200, tmp_path, monkeypatch):
+    n = 50000
+    _write_tab(str(tmp_path / "milkyway_andromeda.tab"), n, seed=11)
+    monkeypatch.chdir(tmp_path)  # the reference opens the file relative to the CWD (Bodies.cpp:85)
+    ref = ctypes.CDLL(os.path.join(REPO, "oracle", "_ref", "libmurbref.so"))
+    ref.ref_init_bodies.argtypes = [ctypes.c_uint64, ctypes.c_char_p] + [FP] * 8
+    r = {k: np.empty(n, np.float32) for k in KEYS}
+    ref.ref_init_bodies(n, b"milkyway", *[r[k].ctypes.data_as(FP) for k in KEYS])
+    d = b200.load_tab(str(tmp_path / "milkyway_andromeda.tab"))
+    for k in KEYS:
+        assert np.array_equal(r[k].view(np.uint32), d[k].view(np.uint32)), k
