@@ -1,0 +1,55 @@
+"""Multi-process parity worker (launched by tests/test_gpu_parity.py::test_torchrun_ranks_match_single_gpu through
+`python -m torch.distributed.run --nproc-per-node P`): every rank owns one GPU and one shard (b200nb_create_rank, NCCL id
+broadcast over torch.distributed); rank 0 also runs the same problem on a single-GPU context and compares state,
+accelerations and energy.  Exercises the ncclAllGather exchange, the collective downloads and the energy all-reduce."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "nbody-eurohpc_b200"))
+import b200nb  # noqa: E402
+from b200nb import dist as bdist  # noqa: E402
+
+SOFT, DT = 2e8, 3600.0
+
+
+def main():
+    rank, world, local_rank = bdist.env_rank()
+    dist = bdist.init_process_group()
+    nccl_id = bdist.broadcast_bytes(dist, b200nb.Context.unique_id() if rank == 0 else None)
+    ok = True
+    for n, scheme in ((30000, "galaxy"), (4097, "random")):
+        d = b200nb.init_bodies(scheme, n)
+        for integ in (0, 1):
+            ctx = b200nb.Context(n, b200nb.G_F32, SOFT, rank=rank, n_ranks=world, device=local_rank, nccl_id=nccl_id)
+            ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+            ctx.step(DT, integ, 4)
+            state = ctx.download_state()      # collective
+            acc = ctx.download_accel()        # collective
+            energy = ctx.energy()             # collective
+            ctx.close()
+            if rank == 0:
+                with b200nb.Context(n, b200nb.G_F32, SOFT, rank=0, n_ranks=1, device=local_rank) as one:
+                    one.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+                    one.step(DT, integ, 4)
+                    s1, a1, e1 = one.download_state(), one.download_accel(), one.energy()
+                scale = max(float(np.abs(s1[c]).max()) for c in ("qx", "qy", "qz"))
+                for c in ("qx", "qy", "qz"):
+                    ok &= bool(np.all(np.abs(state[c].astype(np.float64) - s1[c]) <= 1e-6 * scale))
+                for c in ("vx", "vy", "vz"):
+                    ok &= bool(np.all(np.abs(state[c].astype(np.float64) - s1[c]) <= 1e-5 * float(np.abs(s1[c]).max())))
+                num = np.linalg.norm(np.stack(acc).astype(np.float64) - np.stack(a1), axis=0)
+                den = np.linalg.norm(np.stack(a1).astype(np.float64), axis=0)
+                ok &= bool(np.max(num / den) <= 2e-6)
+                ok &= abs(energy - e1) <= 1e-6 * abs(e1)
+                print(f"n={n} {scheme} integrator={integ}: max|da|/|a| {np.max(num / den):.2e}, dE {abs(energy - e1) / abs(e1):.1e}, ok={ok}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -244,6 +244,19 @@ def test_two_gpus_match_one(b200, oracle, integrator):
     assert abs(outs[0][2] - outs[1][2]) <= 1e-6 * abs(outs[0][2])
 
 
+def test_torchrun_ranks_match_single_gpu():
+    """One process per GPU (what bench.py --gpus N uses): 2 ranks under torchrun against a single-GPU context."""
+    if _n_devices() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sys
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(REPO, "tests", "mp_rank_parity.py")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok=True") == 4
+
+
 # ------------------------------------------------------------------------------------------------ reference-side binaries
 def _ref_bin(name):
     p = os.path.join(REPO, "oracle", "_ref", name)
