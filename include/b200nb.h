@@ -56,7 +56,8 @@ int b200nb_create(b200nb_ctx **out, uint64_t n_bodies, int n_gpus, float G, floa
 
 /* One process per GPU (torchrun style): this process owns shard `rank` of `n_ranks` on CUDA device `device`.
  * nccl_id is the 128-byte ncclUniqueId made by b200nb_comm_unique_id() on rank 0 and broadcast by the caller
- * (ignored, may be NULL, when n_ranks == 1).  Collective over all ranks when n_ranks > 1.
+ * (ignored, may be NULL, when n_ranks == 1); like any ncclUniqueId it is good for ONE context — make a fresh one
+ * for every b200nb_create_rank.  Collective over all ranks when n_ranks > 1.
  * Replaces: MPI_Init + buildCountsDispls in SimulationNBodyMultiNode.cpp:62-91. */
 int b200nb_create_rank(b200nb_ctx **out, uint64_t n_bodies, float G, float soft, int rank, int n_ranks, int device,
                        const void *nccl_id);

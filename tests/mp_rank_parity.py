@@ -18,11 +18,12 @@ SOFT, DT = 2e8, 3600.0
 def main():
     rank, world, local_rank = bdist.env_rank()
     dist = bdist.init_process_group()
-    nccl_id = bdist.broadcast_bytes(dist, b200nb.Context.unique_id() if rank == 0 else None)
     ok = True
     for n, scheme in ((30000, "galaxy"), (4097, "random")):
         d = b200nb.init_bodies(scheme, n)
         for integ in (0, 1):
+            # an ncclUniqueId creates exactly one communicator: a fresh one per context
+            nccl_id = bdist.broadcast_bytes(dist, b200nb.Context.unique_id() if rank == 0 else None)
             ctx = b200nb.Context(n, b200nb.G_F32, SOFT, rank=rank, n_ranks=world, device=local_rank, nccl_id=nccl_id)
             ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
             ctx.step(DT, integ, 4)
