@@ -241,8 +241,11 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     }
     const Shard &s0 = c->shards[0];
     const uint32_t ti = c->kv->threads * c->kv->r;
+    // rows of partial sums cost 12*L bytes each: never more than MAX_ROWS, never more than 1 GiB in total
+    const uint64_t row_bytes = 12ull * c->L;
+    const uint32_t max_rows = (uint32_t)std::max<uint64_t>((uint64_t)n_ranks, std::min<uint64_t>(MAX_ROWS, (1ull << 30) / row_bytes));
     c->k_per_slice = plan_chunks((uint32_t)(c->L / ti), (uint32_t)(c->L / BLK), (uint32_t)(s0.n_sms * s0.occ),
-                                 (uint32_t)n_ranks, MAX_ROWS, (uint32_t)(4 * c->kv->tjb)).n_chunks;
+                                 (uint32_t)n_ranks, max_rows, (uint32_t)(4 * c->kv->tjb)).n_chunks;
     c->rows = c->k_per_slice * n_ranks;
     for (auto &s : c->shards)
         if (int rc = alloc_buffers(c, s)) return bail(rc);
