@@ -28,6 +28,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(REPO, "nbody-eurohpc_b200"))
 
 SOFT, DT = 2e8, 3600.0
+STRONG_SCALING_BODIES = 4194304
 N_SMS, FP32_LANES = 148, 128
 PIPE_SLOTS_PER_INTERACTION = 12  # 3 FADD + 6 FFMA + 3 FMUL; + 1 MUFU.RSQ on its own pipe
 METRIC = "billion body-interactions/s (N^2 ordered pairs per force pass, self included)"
@@ -379,12 +380,32 @@ def run_b200_arm(args, rank, world, local_rank):
         "hbm_algorithmic_bytes_per_launch": 28.0 * n / world, "hbm_gbs_algorithmic": 28.0 * n / world / (avg_launch_ms * 1e-3) / 1e9,
     }
     cpu = cpu_reference_rate(args.scheme, 30000, 12.0) if world == 1 and not args.no_cpu else None
+    # The --gpus N>1 lines run the strong-scaling workload (n = 4,194,304).  So that a 1..8 series has a same-workload
+    # 1-GPU point, the single-GPU line also carries the rate on that workload (2 timed steps, ~35 s).
+    scaling_base = None
+    if world == 1 and not args.no_scaling_base and n != STRONG_SCALING_BODIES:
+        ctx.close()
+        nb = STRONG_SCALING_BODIES
+        big = b200nb.init_bodies(args.scheme, nb)
+        with b200nb.Context(nb, b200nb.G_F32, SOFT, 1) as c2:
+            c2.upload(*[big[k] for k in names])
+            c2.step(DT, 0, 1)
+            ms = 0.0
+            for _ in range(2):
+                c2.event_record(0)
+                c2.step(DT, 0, 1)
+                c2.event_record(1)
+                ms += c2.event_elapsed_ms(0, 1)
+        scaling_base = {"bodies": nb, "n_gpus": 1, "value": float(nb) ** 2 * 2 / (ms * 1e-3) / 1e9, "unit": "G-int/s",
+                        "ms_per_step": ms / 2, "steps": 2, "warmup": 1,
+                        "note": "same workload as the --gpus N>1 lines (BASELINE configs[4]); efficiency(N) = value(N) / (N * this)"}
     out = {
         "metric": METRIC, "value": value, "unit": "G-int/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (reference Bodies generator restated, srand(0))",
         "config": {"workload": f"murb -n {n} -i {args.steps} --nv --im gpu+b200 --gf  ({args.scheme}, soft {SOFT:g}, dt {DT:g})"
-                   + ("" if world == 1 else f"; targets sharded over {world} GPUs, ncclAllGather of positions per step"),
+                   + ("" if world == 1 else f"; targets sharded over {world} GPUs, ncclAllGather of positions per step; the 1-GPU "
+                      "rate on this workload is the `strong_scaling_base` of the --gpus 1 line"),
                    "bodies": n, "scheme": args.scheme, "integrator": "murb-explicit",
                    "l2": "256 MiB memset between timed steps (outside the per-step event pair); inputs are 16 B/body and L2-resident by design",
                    "timing": "sum over steps of CUDA-event pairs on the library's compute stream, max over ranks"},
@@ -398,6 +419,8 @@ def run_b200_arm(args, rank, world, local_rank):
     }
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    if scaling_base is not None:
+        out["strong_scaling_base"] = scaling_base
     out_guard.emit(json.dumps(out))
     ctx.close()
     if dist is not None:
@@ -414,6 +437,7 @@ def main():
     ap.add_argument("--bodies", type=int, default=None)
     ap.add_argument("--scheme", default="galaxy", choices=["galaxy", "random"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-scaling-base", action="store_true", help="skip the 1-GPU run of the strong-scaling workload")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -424,7 +448,7 @@ def main():
         raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
                          "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
     if args.bodies is None:
-        args.bodies = 200000 if args.gpus <= 1 else 4194304
+        args.bodies = 200000 if args.gpus <= 1 else STRONG_SCALING_BODIES
     if args.steps is None:
         args.steps = 200 if args.gpus <= 1 else 5
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
