@@ -127,6 +127,8 @@ def ic_checksums():
 @pytest.fixture(scope="session")
 def b200():
     import b200nb
+    if not os.path.exists(b200nb.lib_path()):  # fresh checkout: build the product library (nvcc cross-compiles without a GPU)
+        subprocess.check_call(["make", "-C", REPO, "lib"])
     return b200nb
 
 
