@@ -109,7 +109,19 @@ struct Shard {
 
 } // namespace
 
+// A captured run of `steps` consecutive iterations (force + integrator launches) for one (integrator, dt).
+struct StepGraph {
+    int integrator = 0;
+    float dt = 0.f;
+    int steps = 0;
+    uint64_t launches = 0; // kernels inside the graph
+    cudaGraphExec_t exec = nullptr;
+};
+constexpr int GRAPH_STEPS = 16;     // iterations per graph launch
+constexpr int GRAPH_MIN_STEPS = 32; // only worth capturing for longer runs
+
 struct b200nb_ctx {
+    std::vector<StepGraph> graphs;
     uint64_t n = 0;
     int n_ranks = 1;
     uint64_t L = 0, total_pad = 0, stage_stride = 0;
@@ -457,6 +469,8 @@ void b200nb_destroy(b200nb_ctx *c)
 {
     if (!c) return;
     DeviceGuard guard;
+    for (auto &g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto &s : c->shards) {
         if (cudaSetDevice(s.device) != cudaSuccess) continue;
         if (s.s_compute) cudaStreamSynchronize(s.s_compute);
@@ -537,6 +551,57 @@ int b200nb_download_accel(b200nb_ctx *c, float *ax, float *ay, float *az)
     return download_sliced(c, &Shard::acc, ax, ay, az);
 }
 
+// one iteration, enqueued on the compute stream(s)
+static int enqueue_one_step(b200nb_ctx *c, float dt, int integrator)
+{
+    if (integrator == B200NB_INTEGRATOR_MURB) {
+        if (int rc = enqueue_force(c)) return rc;
+        if (int rc = enqueue_integrate(c, IM_MURB, dt)) return rc;
+        if (int rc = enqueue_gather(c)) return rc;
+        c->acc_valid = false; // acc belongs to the positions before the update
+    } else {
+        if (!c->acc_valid) { // a(x_0): once after an upload
+            if (int rc = enqueue_force(c)) return rc;
+            if (int rc = enqueue_integrate(c, IM_REDUCE_ONLY, dt)) return rc;
+        }
+        if (int rc = enqueue_integrate(c, IM_LF_KICK_DRIFT, dt)) return rc;
+        if (int rc = enqueue_gather(c)) return rc;
+        if (int rc = enqueue_force(c)) return rc;
+        if (int rc = enqueue_integrate(c, IM_LF_KICK, dt)) return rc;
+        c->acc_valid = true; // acc == a(x_{n+1})
+    }
+    return B200NB_OK;
+}
+
+// Long single-GPU runs replay a captured CUDA graph of GRAPH_STEPS iterations: at murb-test sizes (N ~ 2k) an
+// iteration is a few microseconds of GPU work behind two launches, so launch latency is the whole cost.
+static int get_step_graph(b200nb_ctx *c, float dt, int integrator, StepGraph **out)
+{
+    for (auto &g : c->graphs)
+        if (g.integrator == integrator && g.dt == dt && g.steps == GRAPH_STEPS) { *out = &g; return B200NB_OK; }
+    Shard &s = c->shards[0];
+    CU(c, cudaSetDevice(s.device));
+    const uint64_t before = c->launches;
+    const bool acc_valid = c->acc_valid;
+    CU(c, cudaStreamBeginCapture(s.s_compute, cudaStreamCaptureModeThreadLocal));
+    int rc = B200NB_OK;
+    for (int i = 0; i < GRAPH_STEPS && rc == B200NB_OK; ++i) rc = enqueue_one_step(c, dt, integrator);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s.s_compute, &graph);
+    StepGraph g;
+    g.integrator = integrator; g.dt = dt; g.steps = GRAPH_STEPS; g.launches = c->launches - before;
+    c->launches = before;      // nothing ran yet
+    c->acc_valid = acc_valid;
+    if (rc != B200NB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(c, B200NB_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(c, B200NB_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+    c->graphs.push_back(g);
+    *out = &c->graphs.back();
+    return B200NB_OK;
+}
+
 int b200nb_step(b200nb_ctx *c, float dt, int integrator, int n_steps)
 {
     if (!c) return B200NB_EINVAL;
@@ -545,24 +610,25 @@ int b200nb_step(b200nb_ctx *c, float dt, int integrator, int n_steps)
         return fail(c, B200NB_EINVAL, "unknown integrator %d", integrator);
     if (n_steps < 0) return fail(c, B200NB_EINVAL, "n_steps < 0");
     DeviceGuard guard;
-    for (int it = 0; it < n_steps; ++it) {
-        if (integrator == B200NB_INTEGRATOR_MURB) {
-            if (int rc = enqueue_force(c)) return rc;
-            if (int rc = enqueue_integrate(c, IM_MURB, dt)) return rc;
-            if (int rc = enqueue_gather(c)) return rc;
-            c->acc_valid = false; // acc belongs to the positions before the update
-        } else {
-            if (!c->acc_valid) { // a(x_0): once after an upload
-                if (int rc = enqueue_force(c)) return rc;
-                if (int rc = enqueue_integrate(c, IM_REDUCE_ONLY, dt)) return rc;
-            }
-            if (int rc = enqueue_integrate(c, IM_LF_KICK_DRIFT, dt)) return rc;
-            if (int rc = enqueue_gather(c)) return rc;
-            if (int rc = enqueue_force(c)) return rc;
-            if (int rc = enqueue_integrate(c, IM_LF_KICK, dt)) return rc;
-            c->acc_valid = true; // acc == a(x_{n+1})
+    int it = 0;
+    static const bool no_graph = getenv("B200NB_NO_GRAPH") != nullptr;
+    if (c->n_ranks == 1 && !c->profiling && !no_graph && n_steps >= GRAPH_MIN_STEPS) {
+        if (integrator == B200NB_INTEGRATOR_LEAPFROG && !c->acc_valid) { // the one-off a(x_0) pass stays outside the graph
+            if (int rc = enqueue_one_step(c, dt, integrator)) return rc;
+            ++it;
         }
+        StepGraph *g = nullptr;
+        if (int rc = get_step_graph(c, dt, integrator, &g)) return rc;
+        Shard &s = c->shards[0];
+        CU(c, cudaSetDevice(s.device));
+        for (; it + GRAPH_STEPS <= n_steps; it += GRAPH_STEPS) {
+            CU(c, cudaGraphLaunch(g->exec, s.s_compute));
+            c->launches += g->launches;
+        }
+        c->acc_valid = integrator == B200NB_INTEGRATOR_LEAPFROG;
     }
+    for (; it < n_steps; ++it)
+        if (int rc = enqueue_one_step(c, dt, integrator)) return rc;
     return B200NB_OK;
 }
 

@@ -187,6 +187,25 @@ def test_energy_matches_oracle_and_leapfrog_conserves(b200, oracle):
     assert drift[1] < 1e-3 and drift[1] <= drift[0], drift
 
 
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_graph_replay_is_bit_identical(b200, oracle, integrator, monkeypatch):
+    """b200nb_step(n_steps >= 32) replays a captured CUDA graph of 16 iterations; it must be the same arithmetic as
+    stepping one iteration at a time."""
+    n = 3000
+    d = oracle.init_bodies("random", n)
+    with make_ctx(b200, d) as ctx:
+        for _ in range(70):
+            ctx.step(DT, integrator, 1)
+        ref = ctx.download_state()
+        ref_launches = ctx.launch_count
+    with make_ctx(b200, d) as ctx:
+        ctx.step(DT, integrator, 70)   # 4 graph launches + 6 (or 5) eager iterations
+        got = ctx.download_state()
+        assert ctx.launch_count == ref_launches
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(ref[k].view(np.uint32), got[k].view(np.uint32)), k
+
+
 # ------------------------------------------------------------------------------------------------ API behaviour
 def test_state_errors(b200, oracle):
     ctx = b200.Context(100, G_F32, SOFT)
