@@ -73,19 +73,22 @@ struct KernelVariant {
     ForceKernelFn fn;
     int threads, r, tjb, st;
     size_t smem;
+    double int_per_clk_sm; // measured steady-state rate (profiles/), used to choose between variants for small N
 };
-#define VARIANT(NAME, THREADS, R, TJB, ST, MATH, WP, U, MINB)                                                        \
+#define VARIANT(NAME, THREADS, R, TJB, ST, MATH, WP, U, MINB, RATE)                                                  \
     KernelVariant { NAME, force_kernel<THREADS, R, TJB, ST, MATH, WP, U, MINB>, THREADS, R, TJB, ST,                 \
-                    force_smem_bytes<THREADS, R, TJB, ST, WP>() }
+                    force_smem_bytes<THREADS, R, TJB, ST, WP>(), RATE }
 const KernelVariant g_variants[] = {
     // default first; chosen from the B200 sweep in profiles/ (tools/kbench)
     // 8 targets per thread and only 2 warps per scheduler: the operand-reuse cache keeps hitting while one warp keeps
     // issuing, which is what gets the accumulate FFMA2 triples back to 2 cycles
-    VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, false, 1, 2),
-    VARIANT("pk_t128_r8_tj4_st2_cta_u1_mb2", 128, 8, 4, 2, 1, false, 1, 2),
-    VARIANT("pk_t256_r8_tj2_st3_cta_u1_mb1", 256, 8, 2, 3, 1, false, 1, 1),
-    VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3),
-    VARIANT("sc_t256_r4_tj2_st3_cta_u1_mb2", 256, 4, 2, 3, 0, false, 1, 2),
+    VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, false, 1, 2, 9.5),
+    // small systems: 256-target tiles and 1-block stages give enough CTAs to fill 148 SMs below N ~ 30k
+    VARIANT("pk_t128_r2_tj1_st3_cta_u2_mb4", 128, 2, 1, 3, 1, false, 2, 4, 8.8),
+    VARIANT("pk_t128_r8_tj4_st2_cta_u1_mb2", 128, 8, 4, 2, 1, false, 1, 2, 9.5),
+    VARIANT("pk_t256_r8_tj2_st3_cta_u1_mb1", 256, 8, 2, 3, 1, false, 1, 1, 9.5),
+    VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3, 9.0),
+    VARIANT("sc_t256_r4_tj2_st3_cta_u1_mb2", 256, 4, 2, 3, 0, false, 1, 2, 8.2),
 };
 constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr uint64_t SLICE_ALIGN = 2048; // multiple of THREADS*R of every variant and of BLK
@@ -217,9 +220,43 @@ const KernelVariant *pick_variant()
             if (!strcmp(e, g_variants[i].name)) return &g_variants[i];
         const long idx = strtol(e, nullptr, 10);
         if (idx >= 0 && idx < N_VARIANTS && e[0] >= '0' && e[0] <= '9') return &g_variants[idx];
-        fprintf(stderr, "libb200nb: unknown B200NB_VARIANT '%s', using %s\n", e, g_variants[0].name);
+        fprintf(stderr, "libb200nb: unknown B200NB_VARIANT '%s', choosing automatically\n", e);
     }
-    return &g_variants[0];
+    return nullptr; // choose by the planner's time estimate (choose_variant)
+}
+
+uint32_t max_rows_for(uint64_t L, int n_ranks)
+{
+    // rows of partial sums cost 12*L bytes each: never more than MAX_ROWS, never more than 1 GiB in total
+    return (uint32_t)std::max<uint64_t>((uint64_t)n_ranks, std::min<uint64_t>(MAX_ROWS, (1ull << 30) / (12ull * L)));
+}
+
+ChunkPlan plan_for(const KernelVariant &kv, uint64_t L, int n_sms, int occ, int n_ranks)
+{
+    const uint32_t ti = kv.threads * kv.r;
+    return plan_chunks((uint32_t)(L / ti), (uint32_t)(L / BLK), (uint32_t)(n_sms * occ), (uint32_t)n_ranks,
+                       max_rows_for(L, n_ranks), (uint32_t)(2 * kv.tjb));
+}
+
+// Between the large-tile default and the small-tile variant, take the one the planner expects to finish first:
+// modelled pass time = (CTA-block-times) x (interactions per CTA-block) / (per-CTA rate = SM rate / resident CTAs).
+int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
+{
+    cudaDeviceProp prop;
+    CU(c, cudaGetDeviceProperties(&prop, device));
+    const KernelVariant *cands[2] = {&g_variants[0], &g_variants[1]};
+    double best_t = 1e300;
+    *out = cands[0];
+    for (const KernelVariant *kv : cands) {
+        int occ = 0;
+        CU(c, cudaFuncSetAttribute(kv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv->smem));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kv->fn, kv->threads, kv->smem));
+        if (occ < 1) continue;
+        const ChunkPlan p = plan_for(*kv, c->L, prop.multiProcessorCount, occ, c->n_ranks);
+        const double t = p.cta_block_times * (double)(kv->threads * kv->r) * (double)occ / kv->int_per_clk_sm;
+        if (t < best_t) { best_t = t; *out = kv; }
+    }
+    return B200NB_OK;
 }
 
 int enqueue_gather(b200nb_ctx *c);
@@ -237,6 +274,9 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     c->n = n; c->n_ranks = n_ranks; c->G = G; c->soft = soft; c->soft2 = soft * soft;
     c->kv = pick_variant();
     c->L = b200nb_slice_length(n, n_ranks);
+    if (!c->kv) {
+        if (int rc = choose_variant(c, devices[0], &c->kv)) { g_create_error = c->err; delete c; return rc; }
+    }
     c->total_pad = c->L * n_ranks;
     c->nblk_total = (uint32_t)(c->total_pad / BLK);
     c->stage_stride = (n + 3) / 4 * 4;
@@ -252,12 +292,7 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
         if (int rc = alloc_shard(c, c->shards[i])) return bail(rc);
     }
     const Shard &s0 = c->shards[0];
-    const uint32_t ti = c->kv->threads * c->kv->r;
-    // rows of partial sums cost 12*L bytes each: never more than MAX_ROWS, never more than 1 GiB in total
-    const uint64_t row_bytes = 12ull * c->L;
-    const uint32_t max_rows = (uint32_t)std::max<uint64_t>((uint64_t)n_ranks, std::min<uint64_t>(MAX_ROWS, (1ull << 30) / row_bytes));
-    c->k_per_slice = plan_chunks((uint32_t)(c->L / ti), (uint32_t)(c->L / BLK), (uint32_t)(s0.n_sms * s0.occ),
-                                 (uint32_t)n_ranks, max_rows, (uint32_t)(4 * c->kv->tjb)).n_chunks;
+    c->k_per_slice = plan_for(*c->kv, c->L, s0.n_sms, s0.occ, n_ranks).n_chunks;
     c->rows = c->k_per_slice * n_ranks;
     for (auto &s : c->shards)
         if (int rc = alloc_buffers(c, s)) return bail(rc);

@@ -12,6 +12,7 @@ struct ChunkPlan {
     uint32_t n_chunks;       // chunks per slice (k); the grid has k * n_ranks chunks in total
     uint32_t waves;          // CTA waves of one force pass (both launches when n_ranks > 1)
     double wave_efficiency;  // CTAs / (waves * slots)
+    double cta_block_times;  // modelled duration of the pass in units of "one CTA streaming one 128-source block"
 };
 
 // Cost model fitted to the B200 chunk sweep (profiles/): one pass takes (waves + 1/2) CTA-times — the CTA scheduler
@@ -26,7 +27,7 @@ inline ChunkPlan plan_chunks(uint32_t n_itiles, uint32_t blocks_per_slice, uint3
                              uint32_t max_rows, uint32_t min_blocks_per_chunk = 8)
 {
     const uint32_t k_hi = std::max(1u, std::min(max_rows / std::max(1u, n_ranks), blocks_per_slice / std::max(1u, min_blocks_per_chunk)));
-    ChunkPlan best{1, 1, 0.0};
+    ChunkPlan best{1, 1, 0.0, 0.0};
     double best_t = 1e300;
     for (uint32_t k = 1; k <= k_hi; ++k) {
         const uint64_t m_own = (uint64_t)n_itiles * k, m_rem = m_own * (n_ranks - 1);
@@ -36,7 +37,7 @@ inline ChunkPlan plan_chunks(uint32_t n_itiles, uint32_t blocks_per_slice, uint3
         const double t = ((double)(w_own + w_rem) + tails) * (bpc + 0.3);
         if (t < best_t) {
             best_t = t;
-            best = ChunkPlan{k, (uint32_t)(w_own + w_rem), (double)(m_own + m_rem) / (double)((w_own + w_rem) * slots)};
+            best = ChunkPlan{k, (uint32_t)(w_own + w_rem), (double)(m_own + m_rem) / (double)((w_own + w_rem) * slots), t};
         }
     }
     return best;

@@ -342,7 +342,7 @@ int main(int argc, char **argv)
         const uint32_t ti = v.threads * v.r;
         const uint32_t n_itiles = (uint32_t)(p.n_pad / ti);
         const uint32_t n_blocks = (uint32_t)(p.n_pad / BLK);
-        ChunkPlan plan = plan_chunks(n_itiles, n_blocks, (uint32_t)(sms * occ), 1u, (uint32_t)p.partial_rows, (uint32_t)(4 * v.tjb));
+        ChunkPlan plan = plan_chunks(n_itiles, n_blocks, (uint32_t)(sms * occ), 1u, (uint32_t)p.partial_rows, (uint32_t)(2 * v.tjb));
         if (chunks_override > 0) plan.n_chunks = chunks_override;
         ForceArgs a{};
         a.src = p.d_bodies; a.tgt = p.d_bodies; a.partial = p.d_partial;
