@@ -84,7 +84,7 @@ const KernelVariant g_variants[] = {
     // issuing, which is what gets the accumulate FFMA2 triples back to 2 cycles
     VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, false, 1, 2, 9.5),
     // small systems: 256-target tiles and 1-block stages give enough CTAs to fill 148 SMs below N ~ 30k
-    VARIANT("pk_t128_r2_tj1_st3_cta_u2_mb4", 128, 2, 1, 3, 1, false, 2, 4, 8.8),
+    VARIANT("pk_t128_r2_tj1_st3_cta_u2_mb4", 128, 2, 1, 3, 1, false, 2, 4, 9.2),
     VARIANT("pk_t128_r8_tj4_st2_cta_u1_mb2", 128, 8, 4, 2, 1, false, 1, 2, 9.5),
     VARIANT("pk_t256_r8_tj2_st3_cta_u1_mb1", 256, 8, 2, 3, 1, false, 1, 1, 9.5),
     VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3, 9.0),
