@@ -116,6 +116,19 @@ def test_accel_full_size_properties(b200, oracle, scheme, n):
         assert np.array_equal((acc[k] * np.float32(2)).view(np.uint32), accm[k].view(np.uint32))
 
 
+@pytest.mark.parametrize("soft", [0.035, 1.0e4, 2.0e9])
+def test_accel_other_softenings(b200, oracle, soft):
+    """0.035 is the constructors' default softening (SimulationNBodyInterface.hpp:38): close pairs are practically
+    unsoftened, forces span many orders of magnitude; 2e9 is softening far larger than the system."""
+    n = 6000
+    d = oracle.init_bodies("random", n)
+    with make_ctx(b200, d, soft=soft) as ctx:
+        ctx.accel()
+        acc = ctx.download_accel()
+    assert all(np.all(np.isfinite(a)) for a in acc)
+    assert max_rel_err(oracle.accel_f64(d, soft=soft), acc) <= ACC_TOL
+
+
 def test_zero_mass_and_coincident_bodies(b200, oracle):
     n = 300
     d = oracle.init_bodies("random", n)
