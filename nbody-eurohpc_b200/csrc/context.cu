@@ -92,7 +92,7 @@ const KernelVariant g_variants[] = {
 };
 constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr uint64_t SLICE_ALIGN = 2048; // multiple of THREADS*R of every variant and of BLK
-constexpr uint32_t MAX_ROWS = 64;
+constexpr uint32_t MAX_ROWS = 256; // upper bound on partial rows (the 1 GiB cap in max_rows_for usually binds first for big N)
 constexpr int N_TIMER_SLOTS = 8;
 
 struct Shard {
