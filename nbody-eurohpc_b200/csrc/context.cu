@@ -243,6 +243,7 @@ ChunkPlan plan_for(const KernelVariant &kv, uint64_t L, int n_sms, int occ, int 
 int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
 {
     cudaDeviceProp prop;
+    CU(c, cudaSetDevice(device)); // the occupancy query below answers for the current device
     CU(c, cudaGetDeviceProperties(&prop, device));
     const KernelVariant *cands[2] = {&g_variants[0], &g_variants[1]};
     double best_t = 1e300;
@@ -435,23 +436,24 @@ int download_sliced(b200nb_ctx *c, float *Shard::*field, float *hx, float *hy, f
     // one rank per process: all-gather the slices through a temporary [P][3][L] device buffer
     Shard &s = c->shards[0];
     CU(c, cudaSetDevice(s.device));
-    float *tmp = nullptr;
+    struct Scratch { // freed on every exit path
+        float *p = nullptr;
+        ~Scratch() { if (p) cudaFree(p); }
+    } tmp;
     const size_t count = 3 * (size_t)c->L;
-    CU(c, cudaMalloc((void **)&tmp, count * c->n_ranks * 4));
-    CU(c, cudaMemcpyAsync(tmp + (size_t)s.rank * count, s.*field, count * 4, cudaMemcpyDeviceToDevice, s.s_compute));
-    ncclResult_t r = g_nccl.AllGather(tmp + (size_t)s.rank * count, tmp, count, ncclFloat, s.comm, s.s_compute);
-    if (r != ncclSuccess) { cudaFree(tmp); return fail(c, B200NB_ENCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString(r)); }
+    CU(c, cudaMalloc((void **)&tmp.p, count * c->n_ranks * 4));
+    CU(c, cudaMemcpyAsync(tmp.p + (size_t)s.rank * count, s.*field, count * 4, cudaMemcpyDeviceToDevice, s.s_compute));
+    NC(c, g_nccl.AllGather(tmp.p + (size_t)s.rank * count, tmp.p, count, ncclFloat, s.comm, s.s_compute));
     for (int rk = 0; rk < c->n_ranks; ++rk) {
         const uint64_t first = (uint64_t)rk * c->L;
         if (first >= c->n) break;
         const size_t cnt = (size_t)std::min<uint64_t>(c->L, c->n - first);
         for (int k = 0; k < 3; ++k)
             if (dst[k])
-                CU(c, cudaMemcpyAsync(dst[k] + first, tmp + (size_t)rk * count + (size_t)k * c->L, cnt * 4,
+                CU(c, cudaMemcpyAsync(dst[k] + first, tmp.p + (size_t)rk * count + (size_t)k * c->L, cnt * 4,
                                       cudaMemcpyDeviceToHost, s.s_compute));
     }
     CU(c, cudaStreamSynchronize(s.s_compute));
-    CU(c, cudaFree(tmp));
     return B200NB_OK;
 }
 
