@@ -46,6 +46,28 @@ def main():
                 ok &= bool(np.max(num / den) <= 2e-6)
                 ok &= abs(energy - e1) <= 1e-6 * abs(e1)
                 print(f"n={n} {scheme} integrator={integ}: max|da|/|a| {np.max(num / den):.2e}, dE {abs(energy - e1) / abs(e1):.1e}, ok={ok}", flush=True)
+    # large N, where only sampled targets can be checked on the CPU: fp64 all-pairs oracle (tests/conftest.py)
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from conftest import Oracle, max_rel_err
+    n, scheme = 500000, "random"
+    d = b200nb.init_bodies(scheme, n)
+    nccl_id = bdist.broadcast_bytes(dist, b200nb.Context.unique_id() if rank == 0 else None)
+    ctx = b200nb.Context(n, b200nb.G_F32, SOFT, rank=rank, n_ranks=world, device=local_rank, nccl_id=nccl_id)
+    ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+    ctx.step(DT, 0, 2)          # two exchanges, so the second force pass reads gathered positions
+    ctx.accel()
+    state, acc = ctx.download_state(), ctx.download_accel()
+    ctx.close()
+    if rank == 0:
+        oracle = Oracle(os.path.join(REPO, "oracle", "liboracle.so"))
+        idx = np.unique(np.concatenate([[0, n // world - 1, n // world, n - 1], np.random.default_rng(5).integers(0, n, 60)])).astype(np.uint64)
+        moved = dict(d)
+        moved.update({k: state[k] for k in ("qx", "qy", "qz")})
+        a64 = oracle.accel_f64(moved, idx)
+        err = max_rel_err(a64, [a[idx.astype(np.int64)] for a in acc])
+        good = err <= 1e-5
+        ok &= good
+        print(f"n={n} {scheme} sampled fp64 oracle after 2 sharded steps: max|da|/|a| {err:.2e}, ok={good}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

@@ -286,7 +286,7 @@ def test_torchrun_ranks_match_single_gpu():
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    assert r.stdout.count("ok=True") == 4
+    assert r.stdout.count("ok=True") == 5
 
 
 # ------------------------------------------------------------------------------------------------ reference-side binaries
