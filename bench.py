@@ -133,6 +133,8 @@ def _cpu_model():
 
 def load_reference():
     """Best ISA build of the reference CPU path present in oracle/_ref (built from /root/reference by oracle/build_ref.sh)."""
+    if os.environ.get("B200NB_BENCH_NO_REF"):  # force the oracle-port fallback (tests)
+        return None, None
     flags = _cpu_flags()
     cands = []
     if {"avx512f", "avx512dq", "avx512bw", "avx512vl"} <= flags:
@@ -196,12 +198,11 @@ def cpu_reference_rate(scheme, n_sample, budget_s, tag="cpu+omp"):
 
 def oracle_port_rate(scheme, budget_s):
     """Fallback when oracle/_ref was not built: the scalar C restatement (oracle/liboracle.so), one core."""
-    import subprocess
-    p = os.path.join(REPO, "oracle", "liboracle.so")
-    if not os.path.exists(p):
-        subprocess.check_call(["make", "-C", REPO, "oracle"], stdout=subprocess.DEVNULL)
-    from tests.conftest import Oracle
-    o = Oracle(p)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pyoracle", os.path.join(REPO, "oracle", "pyoracle.py"))
+    pyoracle = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pyoracle)
+    o = pyoracle.load()  # builds oracle/liboracle.so if needed
     n = 8000
     d = o.init_bodies(scheme, n)
     t0 = time.perf_counter()

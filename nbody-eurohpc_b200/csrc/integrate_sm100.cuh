@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
     if (a.mode == IM_MURB || a.mode == IM_MURB_STORED) {
         // The reference writes `q + (v + aDt * 0.5) * dt` with a double literal, so for T=float the position update
         // is evaluated in fp64 and rounded once (Bodies.cpp:264-270, CUDABodies.cu:139-141).  Same here, without
-        // FMA contraction so the result is bit-identical to the host restatement in oracle/.
+        // FMA contraction, so the result is bit-identical to an IEEE host evaluation of the same expression (tested).
         const float axdt = __fmul_rn(ax, a.dt), aydt = __fmul_rn(ay, a.dt), azdt = __fmul_rn(az, a.dt);
         const double dt = (double)a.dt;
         const double qx = (double)a.bodies[ix], qy = (double)a.bodies[iy], qz = (double)a.bodies[iz];

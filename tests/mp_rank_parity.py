@@ -47,8 +47,11 @@ def main():
                 ok &= abs(energy - e1) <= 1e-6 * abs(e1)
                 print(f"n={n} {scheme} integrator={integ}: max|da|/|a| {np.max(num / den):.2e}, dE {abs(energy - e1) / abs(e1):.1e}, ok={ok}", flush=True)
     # large N, where only sampled targets can be checked on the CPU: fp64 all-pairs oracle (tests/conftest.py)
-    sys.path.insert(0, os.path.join(REPO, "tests"))
-    from conftest import Oracle, max_rel_err
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pyoracle", os.path.join(REPO, "oracle", "pyoracle.py"))
+    pyoracle = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pyoracle)
+    max_rel_err = pyoracle.max_rel_err
     n, scheme = 500000, "random"
     d = b200nb.init_bodies(scheme, n)
     nccl_id = bdist.broadcast_bytes(dist, b200nb.Context.unique_id() if rank == 0 else None)
@@ -59,7 +62,7 @@ def main():
     state, acc = ctx.download_state(), ctx.download_accel()
     ctx.close()
     if rank == 0:
-        oracle = Oracle(os.path.join(REPO, "oracle", "liboracle.so"))
+        oracle = pyoracle.load()
         idx = np.unique(np.concatenate([[0, n // world - 1, n // world, n - 1], np.random.default_rng(5).integers(0, n, 60)])).astype(np.uint64)
         moved = dict(d)
         moved.update({k: state[k] for k in ("qx", "qy", "qz")})

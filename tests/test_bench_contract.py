@@ -30,6 +30,14 @@ def test_reference_arm_line():
     assert "workload" in d["config"] and d["value"] > 0
 
 
+def test_reference_arm_falls_back_to_the_oracle_port(monkeypatch):
+    """Without oracle/_ref (the reference could not be compiled) the arm times the oracle's C restatement instead."""
+    monkeypatch.setenv("B200NB_BENCH_NO_REF", "1")
+    d = _run(["--impl", "reference", "--steps", "2", "--warmup", "1"], 600)
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["value"] > 0 and BASE_KEYS - {"ms_per_step"} <= set(d)
+
+
 @pytest.mark.gpu
 def test_b200_arm_line():
     d = _run(["--steps", "5", "--warmup", "3", "--no-cpu", "--no-scaling-base"], 900)

@@ -13,7 +13,6 @@ import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "nbody-eurohpc_b200"))
-sys.path.insert(0, os.path.join(REPO, "tests"))
 import b200nb  # noqa: E402
 
 SOFT, DT = 2e8, 3600.0
@@ -52,8 +51,11 @@ def main():
     for name, e in rows.items():
         print(f"N={args.bodies} {args.scheme} {name}: E0={e[0]:.9e}  max|dE/E0| over {args.iters} it = {np.max(np.abs((e - e[0]) / e[0])):.3e}")
     if args.cpu_check:
-        from conftest import Oracle
-        oracle = Oracle(os.path.join(REPO, "oracle", "liboracle.so"))
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("pyoracle", os.path.join(REPO, "oracle", "pyoracle.py"))
+        pyoracle = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(pyoracle)
+        oracle = pyoracle.load()
         n = args.cpu_check
         gpu = drift_gpu(n, args.scheme, args.iters, args.every)
         for name, integ in (("murb_explicit", 0), ("leapfrog_kdk", 1)):
