@@ -192,6 +192,18 @@ def cpu_reference_rate(scheme, n_sample, budget_s, tag="cpu+omp"):
             ms_t = L.ref_run(t.encode(), n_t, scheme.encode(), SOFT, DT, it, *none)
             others[t] = {"value": float(n_t) ** 2 * it / (ms_t * 1e-3) / 1e9, "unit": "G-int/s", "cores": 1, "n_sample": n_t,
                          "iters": it, "ms_per_iter": ms_t / it}
+        # the same cpu+omp exactly as the reference ships it (no -march: SSE2 MIPP, CMakeLists.txt:128-131)
+        shipped = os.path.join(REPO, "oracle", "_ref", "libmurbref.so")
+        if os.path.exists(shipped) and "as shipped" not in desc:
+            FP = ctypes.POINTER(ctypes.c_float)
+            S = ctypes.CDLL(shipped)
+            S.ref_run.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_float, ctypes.c_float, ctypes.c_int] + [FP] * 9
+            S.ref_run.restype = ctypes.c_double
+            S.ref_run(b"cpu+omp", n_sample, scheme.encode(), SOFT, DT, 1, *none)
+            ms_s = S.ref_run(b"cpu+omp", n_sample, scheme.encode(), SOFT, DT, 10, *none)
+            others["cpu+omp as shipped (-O3 -ffast-math, SSE2 MIPP)"] = {
+                "value": float(n_sample) ** 2 * 10 / (ms_s * 1e-3) / 1e9, "unit": "G-int/s", "cores": cores, "n_sample": n_sample,
+                "iters": 10, "ms_per_iter": ms_s / 10}
         out["other_reference_paths"] = others
     return out
 
