@@ -68,23 +68,30 @@ thread_local std::string g_create_error;
 
 // ------------------------------------------------------------------------------------------------ kernel table
 typedef void (*ForceKernelFn)(const ForceArgs);
+typedef void (*ForceKernelSkFn)(const ForceArgsSK);
 struct KernelVariant {
     const char *name;
     ForceKernelFn fn;
     int threads, r, tjb, st;
     size_t smem;
     double int_per_clk_sm; // measured steady-state rate (profiles/), used to choose between variants for small N
+    ForceKernelSkFn fn_sk; // stream-K decomposition of the same inner loop (nullptr: not built for this variant)
+    size_t smem_sk;
 };
 #define VARIANT(NAME, THREADS, R, TJB, ST, MATH, WP, U, MINB, RATE)                                                  \
     KernelVariant { NAME, force_kernel<THREADS, R, TJB, ST, MATH, WP, U, MINB>, THREADS, R, TJB, ST,                 \
-                    force_smem_bytes<THREADS, R, TJB, ST, WP>(), RATE }
+                    force_smem_bytes<THREADS, R, TJB, ST, WP>(), RATE, nullptr, 0 }
+#define VARIANT_SK(NAME, THREADS, R, TJB, ST, U, MINB, RATE)                                                         \
+    KernelVariant { NAME, force_kernel<THREADS, R, TJB, ST, 1, false, U, MINB>, THREADS, R, TJB, ST,                 \
+                    force_smem_bytes<THREADS, R, TJB, ST, false>(), RATE, force_kernel_sk<THREADS, R, TJB, ST, U, MINB>, \
+                    force_sk_smem_bytes<THREADS, R, TJB, ST>() }
 const KernelVariant g_variants[] = {
     // default first; chosen from the B200 sweep in profiles/ (tools/kbench)
     // 8 targets per thread and only 2 warps per scheduler: the operand-reuse cache keeps hitting while one warp keeps
     // issuing, which is what gets the accumulate FFMA2 triples back to 2 cycles
-    VARIANT("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, false, 1, 2, 9.5),
+    VARIANT_SK("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, 2, 9.5),
     // small systems: 256-target tiles and 1-block stages give enough CTAs to fill 148 SMs below N ~ 30k
-    VARIANT("pk_t128_r2_tj1_st3_cta_u2_mb4", 128, 2, 1, 3, 1, false, 2, 4, 9.2),
+    VARIANT_SK("pk_t128_r2_tj1_st3_cta_u2_mb4", 128, 2, 1, 3, 2, 4, 9.2),
     VARIANT("pk_t128_r8_tj4_st2_cta_u1_mb2", 128, 8, 4, 2, 1, false, 1, 2, 9.5),
     VARIANT("pk_t256_r8_tj2_st3_cta_u1_mb1", 256, 8, 2, 3, 1, false, 1, 1, 9.5),
     VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3, 9.0),
@@ -104,7 +111,7 @@ struct Shard {
     double *energy_blocks = nullptr, *energy_out = nullptr;
     void *l2_scratch = nullptr;
     ncclComm_t comm = nullptr;
-    int n_sms = 0, occ = 0;
+    int n_sms = 0, occ = 0, occ_sk = 0;
     uint32_t n_local = 0; // real bodies in the slice
     std::vector<cudaEvent_t> prof; // pairs (start, stop) around force launches
     uint64_t bytes = 0;
@@ -127,11 +134,15 @@ struct b200nb_ctx {
     std::vector<StepGraph> graphs;
     uint64_t n = 0;
     int n_ranks = 1;
-    uint64_t L = 0, total_pad = 0, stage_stride = 0;
+    uint64_t L = 0, total_pad = 0, stage_stride = 0, total_pad_hint = 0;
     uint32_t nblk_total = 0;
     float G = 0.f, soft = 0.f, soft2 = 0.f;
     const KernelVariant *kv = nullptr;
     uint32_t k_per_slice = 1, rows = 1; // S = k_per_slice * n_ranks
+    std::string kname;                  // variant name (+ "+sk" in stream-K mode)
+    bool stream_k = false;              // stream-K decomposition instead of the (tile x chunk) grid
+    uint32_t sk_grid = 0;               // CTAs per stream-K launch (resident slots)
+    uint32_t sk_rows_own = 0, sk_rows_rem = 0;
     std::vector<Shard> shards;
     bool uploaded = false, acc_valid = false, profiling = false;
     uint64_t launches = 0;
@@ -187,6 +198,10 @@ int alloc_shard(b200nb_ctx *c, Shard &s)
     CU(c, cudaFuncSetAttribute(c->kv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kv->smem));
     CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ, c->kv->fn, c->kv->threads, c->kv->smem));
     if (s.occ < 1) return fail(c, B200NB_ECUDA, "force kernel %s cannot be resident on device %d", c->kv->name, s.device);
+    if (c->kv->fn_sk) {
+        CU(c, cudaFuncSetAttribute(c->kv->fn_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kv->smem_sk));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ_sk, c->kv->fn_sk, c->kv->threads, c->kv->smem_sk));
+    }
     const uint64_t first = (uint64_t)s.rank * c->L;
     s.n_local = first >= c->n ? 0u : (uint32_t)std::min<uint64_t>(c->L, c->n - first);
     return B200NB_OK;
@@ -253,8 +268,22 @@ int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
         CU(c, cudaFuncSetAttribute(kv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv->smem));
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kv->fn, kv->threads, kv->smem));
         if (occ < 1) continue;
-        const ChunkPlan p = plan_for(*kv, c->L, prop.multiProcessorCount, occ, c->n_ranks);
-        const double t = p.cta_block_times * (double)(kv->threads * kv->r) * (double)occ / kv->int_per_clk_sm;
+        const char *mode = getenv("B200NB_MODE");
+        double t;
+        if (kv->fn_sk && !(mode && !strcmp(mode, "grid"))) {
+            // stream-K: every CTA gets ceil(U/G) (tile x block) units; a unit is TI x 128 interactions at SM rate / occ
+            int occ_sk = 0;
+            CU(c, cudaFuncSetAttribute(kv->fn_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv->smem_sk));
+            CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sk, kv->fn_sk, kv->threads, kv->smem_sk));
+            if (occ_sk < 1) continue;
+            const uint64_t G = (uint64_t)prop.multiProcessorCount * occ_sk;
+            const uint64_t ti = (uint64_t)kv->threads * kv->r;
+            const uint64_t U = (c->L / ti) * (c->total_pad_hint / BLK);
+            t = (double)((U + G - 1) / G) * (double)ti * (double)occ_sk / kv->int_per_clk_sm;
+        } else {
+            const ChunkPlan p = plan_for(*kv, c->L, prop.multiProcessorCount, occ, c->n_ranks);
+            t = p.cta_block_times * (double)(kv->threads * kv->r) * (double)occ / kv->int_per_clk_sm;
+        }
         if (t < best_t) { best_t = t; *out = kv; }
     }
     return B200NB_OK;
@@ -275,6 +304,7 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     c->n = n; c->n_ranks = n_ranks; c->G = G; c->soft = soft; c->soft2 = soft * soft;
     c->kv = pick_variant();
     c->L = b200nb_slice_length(n, n_ranks);
+    c->total_pad_hint = c->L * n_ranks;
     if (!c->kv) {
         if (int rc = choose_variant(c, devices[0], &c->kv)) { g_create_error = c->err; delete c; return rc; }
     }
@@ -295,6 +325,27 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     const Shard &s0 = c->shards[0];
     c->k_per_slice = plan_for(*c->kv, c->L, s0.n_sms, s0.occ, n_ranks).n_chunks;
     c->rows = c->k_per_slice * n_ranks;
+    {
+        const char *mode = getenv("B200NB_MODE"); // "grid" | "sk"
+        c->stream_k = c->kv->fn_sk && s0.occ_sk >= 1 && !(mode && !strcmp(mode, "grid"));
+        if (mode && !strcmp(mode, "sk") && !c->stream_k) { c->err = "B200NB_MODE=sk: variant has no stream-K kernel"; return bail(B200NB_EINVAL); }
+    }
+    c->kname = std::string(c->kv->name) + (c->stream_k ? "+sk" : "");
+    if (c->stream_k) {
+        const uint32_t ti = c->kv->threads * c->kv->r;
+        const uint32_t n_itiles = (uint32_t)(c->L / ti), nbs = (uint32_t)(c->L / BLK);
+        c->sk_grid = (uint32_t)(s0.n_sms * s0.occ_sk);
+        auto max_rows = [&](uint32_t nb) {
+            uint32_t m = 0;
+            if (nb == 0) return m;
+            const uint64_t U = (uint64_t)n_itiles * nb;
+            for (uint32_t t = 0; t < n_itiles; ++t) m = std::max(m, sk_rows_of_tile(t, nb, U, c->sk_grid));
+            return m;
+        };
+        c->sk_rows_own = max_rows(nbs);
+        c->sk_rows_rem = max_rows(c->nblk_total - nbs);
+        c->rows = c->sk_rows_own + c->sk_rows_rem;
+    }
     for (auto &s : c->shards)
         if (int rc = alloc_buffers(c, s)) return bail(rc);
 
@@ -324,9 +375,47 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     return B200NB_OK;
 }
 
+// stream-K launches: one for the rank's own (already resident) source blocks, one for the gathered remote blocks
+int enqueue_force_sk(b200nb_ctx *c)
+{
+    const KernelVariant &kv = *c->kv;
+    const uint32_t ti = kv.threads * kv.r;
+    const uint32_t nbs = (uint32_t)(c->L / BLK);
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        ForceArgsSK a{};
+        a.src = s.bodies; a.tgt = s.bodies; a.partial = s.partial;
+        a.tgt_blk0 = (uint32_t)((uint64_t)s.rank * c->L / BLK);
+        a.tgt_stride = (uint32_t)c->L;
+        a.src_nblk_total = c->nblk_total;
+        a.blk_rot = nbs * (uint32_t)s.rank;
+        a.n_itiles = (uint32_t)(c->L / ti);
+        a.soft2 = c->soft2;
+        auto launch = [&](uint32_t lb0, uint32_t nb, uint32_t row0) -> cudaError_t {
+            a.lb0 = lb0; a.nb = nb; a.row0 = row0;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (c->profiling) {
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaEventRecord(e0, s.s_compute);
+            }
+            kv.fn_sk<<<c->sk_grid, kv.threads, kv.smem_sk, s.s_compute>>>(a);
+            if (c->profiling) { cudaEventRecord(e1, s.s_compute); s.prof.push_back(e0); s.prof.push_back(e1); }
+            c->launches++;
+            return cudaGetLastError();
+        };
+        CU(c, launch(0, nbs, 0)); // own slice: resident, overlaps the all-gather
+        if (c->n_ranks > 1) {
+            CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0)); // remote slices must have landed
+            CU(c, launch(nbs, c->nblk_total - nbs, c->sk_rows_own));
+        }
+    }
+    return B200NB_OK;
+}
+
 // enqueue the force pass (own chunks, wait for the gather, remote chunks) on every shard's compute stream
 int enqueue_force(b200nb_ctx *c)
 {
+    if (c->stream_k) return enqueue_force_sk(c);
     const KernelVariant &kv = *c->kv;
     const uint32_t ti = kv.threads * kv.r;
     for (auto &s : c->shards) {
@@ -373,6 +462,13 @@ int enqueue_integrate(b200nb_ctx *c, int mode, float dt)
         a.bodies = s.bodies; a.vel = s.vel; a.acc = s.acc; a.partial = s.partial;
         a.rows = c->rows; a.L = (uint32_t)c->L; a.n_local = s.n_local;
         a.first = (uint64_t)s.rank * c->L; a.dt = dt; a.mode = mode;
+        if (c->stream_k) {
+            const uint32_t ti = c->kv->threads * c->kv->r, n_itiles = (uint32_t)(c->L / ti), nbs = (uint32_t)(c->L / BLK);
+            a.sk_ti = ti;
+            a.sk[0] = SkRows{(uint64_t)n_itiles * nbs, c->sk_grid, nbs, 0};
+            const uint32_t nbr = c->nblk_total - nbs;
+            a.sk[1] = SkRows{(uint64_t)n_itiles * nbr, c->sk_grid, nbr, c->sk_rows_own};
+        }
         integrate_kernel<<<(s.n_local + 255) / 256, 256, 0, s.s_compute>>>(a);
         c->launches++;
         CU(c, cudaGetLastError());
@@ -756,7 +852,7 @@ uint64_t b200nb_allocated_bytes(const b200nb_ctx *c)
     return b;
 }
 uint64_t b200nb_launch_count(const b200nb_ctx *c) { return c ? c->launches : 0; }
-const char *b200nb_kernel_name(const b200nb_ctx *c) { return c ? c->kv->name : ""; }
+const char *b200nb_kernel_name(const b200nb_ctx *c) { return c ? c->kname.c_str() : ""; }
 
 int b200nb_event_record(b200nb_ctx *c, int slot)
 {

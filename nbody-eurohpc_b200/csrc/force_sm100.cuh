@@ -414,4 +414,172 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
     }
 }
 
+
+// =========================================================================================== stream-K decomposition
+// The same inner loop, different work decomposition.  Work unit = (target tile, one 128-source block); a launch has
+// U = n_itiles * nb units and exactly G CTAs (one per resident slot: SMs x CTAs/SM); CTA c takes the contiguous unit
+// range [c*U/G, (c+1)*U/G).  All CTAs are resident at once and get equal work (+-1 unit), so there is no wave
+// quantisation and no tail, for any N.  A CTA's range cuts into at most a few (tile, block-range) segments; each
+// segment writes ONE partial row (row = ordinal of the segment inside its tile, computed in closed form), so a tile has
+// ~2-3 rows instead of one per chunk.  Everything is static: results stay deterministic.
+// Accuracy: segments are long (thousands of blocks at N=1M), so the fp32 second-level accumulator is folded into a
+// per-CTA fp64 accumulator in shared memory every SK_FLUSH_TILES tiles (FP64 pipe, off the FMA pipe; no registers).
+struct ForceArgsSK {
+    const float *src;          // blocked bodies the sources are read from
+    const float *tgt;          // blocked bodies the targets are read from
+    float *partial;            // [rows][3][tgt_stride]
+    uint32_t tgt_blk0;         // first target block inside `tgt`
+    uint32_t tgt_stride;       // floats per component row of `partial`
+    uint32_t src_nblk_total;   // NB: blocks of the whole padded system
+    uint32_t blk_rot;          // logical -> physical block rotation (rank's first block): phys = (lb + rot) % NB
+    uint32_t lb0, nb;          // logical block range [lb0, lb0 + nb) of this launch
+    uint32_t n_itiles;         // target tiles of this rank
+    uint32_t row0;             // first partial row of this launch
+    float soft2;
+};
+
+constexpr int SK_FLUSH_TILES = 32;
+
+// CTA that owns unit x when CTA c owns [c*U/G, (c+1)*U/G)
+__host__ __device__ __forceinline__ uint32_t sk_cta_of(uint64_t x, uint64_t U, uint32_t G)
+{
+    return (uint32_t)(((x + 1) * G - 1) / U);
+}
+// partial rows tile t receives from a launch with U units, nb blocks per tile, G CTAs
+__host__ __device__ __forceinline__ uint32_t sk_rows_of_tile(uint32_t t, uint32_t nb, uint64_t U, uint32_t G)
+{
+    const uint64_t first = (uint64_t)t * nb;
+    return sk_cta_of(first + nb - 1, U, G) - sk_cta_of(first, U, G) + 1;
+}
+
+template <int THREADS, int R, int TJB, int ST>
+constexpr size_t force_sk_smem_bytes()
+{
+    return (size_t)ST * (TJB * BLK_BYTES + 8) + (size_t)3 * THREADS * R * sizeof(double);
+}
+
+template <int THREADS, int R, int TJB, int ST, int U, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_kernel_sk(const ForceArgsSK a)
+{
+    constexpr int TI = THREADS * R;
+    static_assert(TI % BLK == 0, "target tile must cover whole blocks");
+    constexpr int STAGE_FLOATS = TJB * BLK_FLOATS;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *stages = reinterpret_cast<float *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ST * STAGE_FLOATS * 4);
+    double *sacc = reinterpret_cast<double *>(smem_raw + (size_t)ST * (STAGE_FLOATS * 4 + 8)); // [3][TI]
+
+    const bool leader = threadIdx.x == 0;
+    const uint32_t stages_u32 = smem_u32(stages);
+    const uint32_t bar0 = smem_u32(bars);
+
+    const uint64_t units = (uint64_t)a.n_itiles * a.nb;
+    const uint32_t G = gridDim.x, c = blockIdx.x;
+    uint64_t u = units * c / G;
+    const uint64_t u_end = units * (c + 1) / G;
+    if (u >= u_end) return;
+
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s) mbar_init(bar0 + 8 * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint64_t soft2p = pk2(a.soft2, a.soft2);
+    uint32_t tcount = 0; // pipeline tiles consumed so far by this CTA (stage and phase bookkeeping across runs)
+
+    while (u < u_end) {
+        const uint32_t t = (uint32_t)(u / a.nb);
+        const uint32_t off = (uint32_t)(u - (uint64_t)t * a.nb);
+        const uint32_t len = (uint32_t)min((uint64_t)(a.nb - off), u_end - u);
+        const uint32_t row = a.row0 + (c - sk_cta_of((uint64_t)t * a.nb, units, G));
+
+        float xi[R], yi[R], zi[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const size_t il = (size_t)t * TI + (size_t)k * THREADS + threadIdx.x;
+            const size_t ig = (size_t)a.tgt_blk0 * BLK + il;
+            xi[k] = __ldg(a.tgt + blk_index(ig, 0));
+            yi[k] = __ldg(a.tgt + blk_index(ig, 1));
+            zi[k] = __ldg(a.tgt + blk_index(ig, 2));
+            sacc[(0 * R + k) * THREADS + threadIdx.x] = 0.0;
+            sacc[(1 * R + k) * THREADS + threadIdx.x] = 0.0;
+            sacc[(2 * R + k) * THREADS + threadIdx.x] = 0.0;
+        }
+        float mx[R], my[R], mz[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) mx[k] = my[k] = mz[k] = 0.f;
+
+        auto flush64 = [&]() { // fold the fp32 second level into the CTA's fp64 accumulators (own slots: no sync needed)
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                sacc[(0 * R + k) * THREADS + threadIdx.x] += (double)mx[k];
+                sacc[(1 * R + k) * THREADS + threadIdx.x] += (double)my[k];
+                sacc[(2 * R + k) * THREADS + threadIdx.x] += (double)mz[k];
+                mx[k] = my[k] = mz[k] = 0.f;
+            }
+        };
+
+        // the segment's logical blocks are contiguous; physically they may wrap around the end of the array once
+        const uint32_t p0 = (a.lb0 + off + a.blk_rot) % a.src_nblk_total;
+        const uint32_t len0 = min(len, a.src_nblk_total - p0);
+        for (int part = 0; part < 2; ++part) {
+            const uint32_t pb = part == 0 ? p0 : 0u;
+            const uint32_t nblk = part == 0 ? len0 : len - len0;
+            if (nblk == 0) continue;
+            const float *run_src = a.src + (size_t)pb * BLK_FLOATS;
+            const uint32_t ntiles = (nblk + TJB - 1) / TJB;
+            auto issue = [&](uint32_t tile) {
+                const uint32_t stage = (tcount + tile) % ST;
+                const uint32_t nbk = min((uint32_t)TJB, nblk - tile * TJB);
+                const uint32_t bytes = nbk * BLK_BYTES;
+                const uint32_t bar = bar0 + 8 * stage;
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s(stages_u32 + stage * (STAGE_FLOATS * 4), run_src + (size_t)tile * STAGE_FLOATS, bytes, bar);
+            };
+            __syncthreads(); // every thread is done with the stages of the previous run
+            if (leader)
+                for (uint32_t s = 0; s < (uint32_t)ST && s < ntiles; ++s) issue(s);
+
+            for (uint32_t tl = 0; tl < ntiles; ++tl) {
+                const uint32_t tc = tcount + tl;
+                const uint32_t s = tc % ST;
+                mbar_wait(bar0 + 8 * s, (tc / ST) & 1u);
+                const float *sb = stages + (size_t)s * STAGE_FLOATS;
+                const uint32_t nbk = min((uint32_t)TJB, nblk - tl * TJB);
+                uint64_t ax[R], ay[R], az[R];
+#pragma unroll
+                for (int k = 0; k < R; ++k) ax[k] = ay[k] = az[k] = 0ull;
+                for (uint32_t b = 0; b < nbk; ++b) block_packed<R, U, false>(sb + b * BLK_FLOATS, xi, yi, zi, soft2p, ax, ay, az);
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    float lo, hi;
+                    upk2(ax[k], lo, hi); mx[k] += lo + hi;
+                    upk2(ay[k], lo, hi); my[k] += lo + hi;
+                    upk2(az[k], lo, hi); mz[k] += lo + hi;
+                }
+                if ((tl % SK_FLUSH_TILES) == SK_FLUSH_TILES - 1) flush64();
+                if (tl + ST < ntiles) { // refill the stage we just drained
+                    __syncthreads();
+                    if (leader) issue(tl + ST);
+                }
+            }
+            tcount += ntiles;
+        }
+        flush64();
+
+        const size_t prow = (size_t)row * 3;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const size_t il = (size_t)t * TI + (size_t)k * THREADS + threadIdx.x;
+            a.partial[(prow + 0) * a.tgt_stride + il] = (float)sacc[(0 * R + k) * THREADS + threadIdx.x];
+            a.partial[(prow + 1) * a.tgt_stride + il] = (float)sacc[(1 * R + k) * THREADS + threadIdx.x];
+            a.partial[(prow + 2) * a.tgt_stride + il] = (float)sacc[(2 * R + k) * THREADS + threadIdx.x];
+        }
+        u += len;
+    }
+}
+
 } // namespace b200nb

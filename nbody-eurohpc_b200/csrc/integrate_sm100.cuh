@@ -21,6 +21,12 @@ enum IntegrateMode : int {
     IM_MURB_STORED = 4   // MUrB update with the stored acc (caller-supplied accelerations)
 };
 
+// stream-K launches give every target tile its own number of partial rows (force_sm100.cuh: sk_rows_of_tile)
+struct SkRows {
+    uint64_t units; // U of the launch (0: launch not used)
+    uint32_t G, nb, row0;
+};
+
 struct IntegrateArgs {
     float *bodies;        // blocked full array; the slice [first, first+L) is updated in place
     float *vel;           // [3][L] local velocities
@@ -32,6 +38,8 @@ struct IntegrateArgs {
     uint64_t first;       // global index of the first local body (multiple of BLK)
     float dt;
     int mode;
+    uint32_t sk_ti;       // 0: chunk-grid rows [0, rows); else target-tile size of the stream-K launches below
+    SkRows sk[2];
 };
 
 __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
@@ -47,9 +55,22 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
         // fixed-order fp64 sum of the chunk partials: deterministic, and the top level of the
         // hierarchical summation that keeps the fp32 error independent of N
         double sx = 0.0, sy = 0.0, sz = 0.0;
-        for (uint32_t r = 0; r < a.rows; ++r) {
-            const float *p = a.partial + (size_t)r * 3 * L;
-            sx += (double)p[i]; sy += (double)p[L + i]; sz += (double)p[2 * L + i];
+        if (a.sk_ti == 0) {
+            for (uint32_t r = 0; r < a.rows; ++r) {
+                const float *p = a.partial + (size_t)r * 3 * L;
+                sx += (double)p[i]; sy += (double)p[L + i]; sz += (double)p[2 * L + i];
+            }
+        } else {
+            const uint32_t t = i / a.sk_ti;
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+                if (a.sk[l].units == 0) continue;
+                const uint32_t cnt = sk_rows_of_tile(t, a.sk[l].nb, a.sk[l].units, a.sk[l].G);
+                for (uint32_t r = 0; r < cnt; ++r) {
+                    const float *p = a.partial + (size_t)(a.sk[l].row0 + r) * 3 * L;
+                    sx += (double)p[i]; sy += (double)p[L + i]; sz += (double)p[2 * L + i];
+                }
+            }
         }
         ax = (float)sx; ay = (float)sy; az = (float)sz;
         a.acc[i] = ax; a.acc[L + i] = ay; a.acc[2 * L + i] = az;
