@@ -270,7 +270,7 @@ int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
         if (occ < 1) continue;
         const char *mode = getenv("B200NB_MODE");
         double t;
-        if (kv->fn_sk && !(mode && !strcmp(mode, "grid"))) {
+        if (kv->fn_sk && mode && !strcmp(mode, "sk")) {
             // stream-K: every CTA gets ceil(U/G) (tile x block) units; a unit is TI x 128 interactions at SM rate / occ
             int occ_sk = 0;
             CU(c, cudaFuncSetAttribute(kv->fn_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv->smem_sk));
@@ -326,15 +326,19 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     c->k_per_slice = plan_for(*c->kv, c->L, s0.n_sms, s0.occ, n_ranks).n_chunks;
     c->rows = c->k_per_slice * n_ranks;
     {
-        const char *mode = getenv("B200NB_MODE"); // "grid" | "sk"
-        c->stream_k = c->kv->fn_sk && s0.occ_sk >= 1 && !(mode && !strcmp(mode, "grid"));
-        if (mode && !strcmp(mode, "sk") && !c->stream_k) { c->err = "B200NB_MODE=sk: variant has no stream-K kernel"; return bail(B200NB_EINVAL); }
+        // "grid" (default): dynamic (tile x chunk) grid; "sk": static stream-K split, measured 3-8 % slower on B200
+        // (profiles/r01_streamk_vs_grid.txt) and kept as a tested alternative
+        const char *mode = getenv("B200NB_MODE");
+        const bool want_sk = mode && !strcmp(mode, "sk");
+        c->stream_k = want_sk && c->kv->fn_sk && s0.occ_sk >= 1;
+        if (want_sk && !c->stream_k) { c->err = "B200NB_MODE=sk: variant has no stream-K kernel"; return bail(B200NB_EINVAL); }
     }
     c->kname = std::string(c->kv->name) + (c->stream_k ? "+sk" : "");
     if (c->stream_k) {
         const uint32_t ti = c->kv->threads * c->kv->r;
         const uint32_t n_itiles = (uint32_t)(c->L / ti), nbs = (uint32_t)(c->L / BLK);
-        c->sk_grid = (uint32_t)(s0.n_sms * s0.occ_sk);
+        const char *w = getenv("B200NB_SK_WAVES"); // experiment: CTAs = waves x resident slots
+        c->sk_grid = (uint32_t)(s0.n_sms * s0.occ_sk) * (uint32_t)std::max(1, w ? atoi(w) : 1);
         auto max_rows = [&](uint32_t nb) {
             uint32_t m = 0;
             if (nb == 0) return m;

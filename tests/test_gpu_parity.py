@@ -250,6 +250,29 @@ def test_other_kernel_variants(b200, oracle, variant, monkeypatch):
     assert max_rel_err(oracle.accel_f64(d), acc) <= ACC_TOL
 
 
+@pytest.mark.parametrize("scheme,n", [("galaxy", 2049), ("random", 30000), ("galaxy", 200000)])
+def test_stream_k_mode(b200, oracle, scheme, n, monkeypatch):
+    """B200NB_MODE=sk: the static stream-K decomposition (one CTA per resident slot, fp64 shared-memory second-level
+    sums) must give the same physics as the default chunk grid."""
+    monkeypatch.setenv("B200NB_MODE", "sk")
+    d = oracle.init_bodies(scheme, n)
+    with make_ctx(b200, d) as ctx:
+        assert ctx.kernel_name.endswith("+sk")
+        ctx.accel()
+        acc = ctx.download_accel()
+        ctx.step(DT, 1, 3)
+        st = ctx.download_state()
+    idx = np.unique(np.concatenate([[0, n - 1], np.random.default_rng(2).integers(0, n, 100)])).astype(np.uint64)
+    assert max_rel_err(oracle.accel_f64(d, idx), [a[idx.astype(np.int64)] for a in acc]) <= ACC_TOL
+    monkeypatch.delenv("B200NB_MODE")
+    with make_ctx(b200, d) as ctx:
+        ctx.step(DT, 1, 3)
+        ref = ctx.download_state()
+    scale = max(float(np.abs(ref[c]).max()) for c in ("qx", "qy", "qz"))
+    for c in ("qx", "qy", "qz"):
+        assert np.all(np.abs(st[c].astype(np.float64) - ref[c]) <= 1e-6 * scale), c
+
+
 # ------------------------------------------------------------------------------------------------ multi-GPU (in-process)
 def _n_devices():
     import torch
