@@ -21,9 +21,13 @@ rc=0
 stale() { [ ! -e "$1" ] || [ "$2" -nt "$1" ] || [ "$PKG/glue/SimulationNBodyB200.hpp" -nt "$1" ] || [ "$HERE/include/b200nb.h" -nt "$1" ]; }
 
 echo "== 1. libmurbref (as shipped: no -march => SSE2 MIPP) and ISA-specific builds"
-g++ $REFFLAGS -fPIC -shared $INC "$HERE/oracle/ref_wrap.cpp" $CORE $CPUIMPL -o "$OUT/libmurbref.so" || rc=1
-g++ $REFFLAGS -march=x86-64-v3 -fPIC -shared $INC "$HERE/oracle/ref_wrap.cpp" $CORE $CPUIMPL -o "$OUT/libmurbref_v3.so" || rc=1
-g++ $REFFLAGS -march=x86-64-v4 -fPIC -shared $INC "$HERE/oracle/ref_wrap.cpp" $CORE $CPUIMPL -o "$OUT/libmurbref_v4.so" || rc=1
+for v in "" "_v3:-march=x86-64-v3" "_v4:-march=x86-64-v4"; do
+  suffix=${v%%:*}; march=${v#*:}; [ "$v" = "" ] && march=""
+  so="$OUT/libmurbref$suffix.so"
+  if [ ! -e "$so" ] || [ "$HERE/oracle/ref_wrap.cpp" -nt "$so" ]; then
+    g++ $REFFLAGS $march -fPIC -shared $INC "$HERE/oracle/ref_wrap.cpp" $CORE $CPUIMPL -o "$so" || rc=1
+  fi
+done
 
 echo "== 2. murb_b200 (patched CLI)"
 HAVE_MPI=0; command -v mpicxx >/dev/null 2>&1 && HAVE_MPI=1
