@@ -62,4 +62,5 @@ TESTOBJS=""
 for o in $HOSTOBJS; do case "$o" in *ArgumentsReader*|*Nop.host.o|*SpheresVisuNo*) ;; *) TESTOBJS="$TESTOBJS $o";; esac; done
 g++ "$OBJ/test_main.o" "$OBJ/test_B200.o" $TESTOBJS $objs $LINK -o "$OUT/murb-test-b200" || rc=1
 ls -la "$OUT" | grep -v obj
+[ $rc = 0 ] && touch "$OUT/.stamp"
 exit $rc
