@@ -28,6 +28,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "plan.hpp"
+
 namespace b200nb {
 
 constexpr int BLK = 128;                 // bodies per AoSoA block
@@ -439,18 +441,6 @@ struct ForceArgsSK {
 };
 
 constexpr int SK_FLUSH_TILES = 32;
-
-// CTA that owns unit x when CTA c owns [c*U/G, (c+1)*U/G)
-__host__ __device__ __forceinline__ uint32_t sk_cta_of(uint64_t x, uint64_t U, uint32_t G)
-{
-    return (uint32_t)(((x + 1) * G - 1) / U);
-}
-// partial rows tile t receives from a launch with U units, nb blocks per tile, G CTAs
-__host__ __device__ __forceinline__ uint32_t sk_rows_of_tile(uint32_t t, uint32_t nb, uint64_t U, uint32_t G)
-{
-    const uint64_t first = (uint64_t)t * nb;
-    return sk_cta_of(first + nb - 1, U, G) - sk_cta_of(first, U, G) + 1;
-}
 
 template <int THREADS, int R, int TJB, int ST>
 constexpr size_t force_sk_smem_bytes()

@@ -6,7 +6,23 @@
 #include <algorithm>
 #include <cstdint>
 
+#ifdef __CUDACC__
+#define B200NB_HD __host__ __device__ __forceinline__
+#else
+#define B200NB_HD inline
+#endif
+
 namespace b200nb {
+
+// ---- stream-K ownership arithmetic (used by force_kernel_sk, integrate_kernel and the host planner) ----
+// CTA that owns unit x when CTA c owns the unit range [c*U/G, (c+1)*U/G)
+B200NB_HD uint32_t sk_cta_of(uint64_t x, uint64_t U, uint32_t G) { return (uint32_t)(((x + 1) * G - 1) / U); }
+// partial rows tile t receives from a launch with U units, nb blocks per tile, G CTAs
+B200NB_HD uint32_t sk_rows_of_tile(uint32_t t, uint32_t nb, uint64_t U, uint32_t G)
+{
+    const uint64_t first = (uint64_t)t * nb;
+    return sk_cta_of(first + nb - 1, U, G) - sk_cta_of(first, U, G) + 1;
+}
 
 struct ChunkPlan {
     uint32_t n_chunks;       // chunks per slice (k); the grid has k * n_ranks chunks in total

@@ -13,8 +13,6 @@ HARNESS = r'''
 #include <cstdint>
 #include <cstdlib>
 #include "plan.hpp"
-// the two stream-K helpers are plain integer functions: restate their declarations for a host-only build
-static inline uint32_t sk_cta_of(uint64_t x, uint64_t U, uint32_t G) { return (uint32_t)(((x + 1) * G - 1) / U); }
 int main(int argc, char **argv)
 {
     using namespace b200nb;
@@ -28,7 +26,7 @@ int main(int argc, char **argv)
         for (uint32_t c = 0; c < G; ++c)
             for (uint64_t u = U * c / G; u < U * (c + 1) / G; ++u) bad += sk_cta_of(u, U, G) != c;
         for (uint32_t t = 0; t < n_itiles; ++t) {
-            const uint32_t rows = sk_cta_of((uint64_t)t * nb + nb - 1, U, G) - sk_cta_of((uint64_t)t * nb, U, G) + 1;
+            const uint32_t rows = sk_rows_of_tile(t, nb, U, G);
             if (rows > max_rows) max_rows = rows;
         }
         printf("{\"bad\": %llu, \"max_rows\": %u}\n", (unsigned long long)bad, max_rows);
