@@ -249,7 +249,7 @@ static void make_problem(Problem &p, size_t n, int sms)
     }
     CK(cudaMalloc(&p.d_bodies, blocked.size() * 4));
     CK(cudaMemcpy(p.d_bodies, blocked.data(), blocked.size() * 4, cudaMemcpyHostToDevice));
-    p.partial_rows = 64;
+    p.partial_rows = 128;
     CK(cudaMalloc(&p.d_partial, p.partial_rows * 3 * p.n_pad * 4));
     p.dbg_ctas = 1 << 20;
     CK(cudaMalloc(&p.d_dbg, p.dbg_ctas * 32));
@@ -343,7 +343,7 @@ int main(int argc, char **argv)
         const uint32_t n_itiles = (uint32_t)(p.n_pad / ti);
         const uint32_t n_blocks = (uint32_t)(p.n_pad / BLK);
         ChunkPlan plan = plan_chunks(n_itiles, n_blocks, (uint32_t)(sms * occ), 1u, (uint32_t)p.partial_rows, (uint32_t)(2 * v.tjb));
-        if (chunks_override > 0) plan.n_chunks = chunks_override;
+        if (chunks_override > 0) plan.n_chunks = std::min<uint32_t>((uint32_t)chunks_override, (uint32_t)p.partial_rows); // never past the allocated rows
         ForceArgs a{};
         a.src = p.d_bodies; a.tgt = p.d_bodies; a.partial = p.d_partial;
         a.tgt_blk0 = 0; a.tgt_stride = (uint32_t)p.n_pad;
