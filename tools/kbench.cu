@@ -70,6 +70,12 @@ __global__ void __launch_bounds__(256) ubench(float *out, unsigned long long *cy
                 if (KIND == 15) p[i] = fma2(q[i], q[i], pk2(y[i], y[i])); // 1 pair + scalar broadcast addend (non-dependent)
                 if (KIND == 16) p[i] = sub2(p[i], pk2(y[i], y[i]));    // FADD2 pair - broadcast vector scalar
                 if (KIND == 17) p[i] = mul2(q[i], p[i]);               // FMUL2 2 distinct pairs
+                // MUFU co-issue cost next to FMA-pipe instructions that read 4 / 3 / 2 vector registers
+                if (KIND == 20) { p[i] = fma2(q[i], q[i], p[i]); if ((u % 6) == 5) v[i] = rsqrt_approx(v[i]); }
+                if (KIND == 21) { p[i] = sub2(p[i], pk2(y[i], y[i])); if ((u % 6) == 5) v[i] = rsqrt_approx(v[i]); }
+                if (KIND == 22) { p[i] = fma2(p[i], p[i], pc2); if ((u % 6) == 5) v[i] = rsqrt_approx(v[i]); }
+                if (KIND == 23) { p[i] = fma2(q[i], q[i], p[i]); if ((u % 3) == 2) v[i] = rsqrt_approx(v[i]); }
+                if (KIND == 24) { p[i] = fma2(w[i], q[i], p[i]); if ((u % 6) == 5) v[i] = rsqrt_approx(v[i]); }
                 if (KIND == 5) { // same op mix as one packed interaction pair, fully dependent inside a chain
                     uint64_t dx = sub2(p[i], pc2), dy = sub2(p[i], pc1), dz = sub2(pc1, p[i]);
                     uint64_t d = fma2(dx, dx, pc2);
@@ -316,6 +322,11 @@ int main(int argc, char **argv)
         run_ubench<7, 8>("6 FFMA2 : 1 MUFU", 4, sms, 1.0 + 1.0 / 6, jf);
         run_ubench<8, 8>("64 FFMA : 1 MUFU", 4, sms, 1.0 + 1.0 / 64, jf);
         run_ubench<10, 8>("32 FFMA2 : 1 LDS.128", 4, sms, 1.0 + 1.0 / 32, jf);
+        run_ubench<20, 8>("6 FFMA2(4 vec regs) : 1 MUFU", 4, sms, 1.0 + 1.0 / 6, jf);
+        run_ubench<23, 8>("3 FFMA2(4 vec regs) : 1 MUFU", 4, sms, 1.0 + 1.0 / 3, jf);
+        run_ubench<21, 8>("6 FADD2(3 vec regs) : 1 MUFU", 4, sms, 1.0 + 1.0 / 6, jf);
+        run_ubench<22, 8>("6 FFMA2(2 vec regs) : 1 MUFU", 4, sms, 1.0 + 1.0 / 6, jf);
+        run_ubench<24, 8>("6 FFMA2(6 vec regs) : 1 MUFU", 4, sms, 1.0 + 1.0 / 6, jf);
         run_ubench<5, 4>("mix 12xf32x2+2xMUFU", 4, sms, 14, jf);
         run_ubench<5, 4>("mix 12xf32x2+2xMUFU", 2, sms, 14, jf);
         run_ubench<5, 2>("mix 12xf32x2+2xMUFU", 4, sms, 14, jf);
