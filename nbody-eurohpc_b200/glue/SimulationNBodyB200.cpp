@@ -137,6 +137,7 @@ SimulationNBodyB200::SimulationNBodyB200(const BodiesAllocatorInterface<float> &
     this->allocatedBytes = this->bodies->getAllocatedBytes();
     const char *csv = std::getenv("MURB_B200_METRICS_CSV");
     if (csv && *csv) this->metricsPath = csv;
+    this->hostMirror = envInt("MURB_B200_HOST_MIRROR", 0) != 0;
 }
 
 SimulationNBodyB200::~SimulationNBodyB200()
@@ -165,6 +166,7 @@ void SimulationNBodyB200::computeOneIteration()
     // main.cpp:353-371 joins the current device only; with several GPUs the others are joined here
     if (b200nb_n_local_gpus(c) > 1) check(b200nb_sync(c), c, "b200nb_sync");
     this->b200Bodies->invalidateDataSoA();
+    if (this->hostMirror) (void)this->b200Bodies->getDataSoA(); // in place: the vectors never move, captured pointers stay valid
     if (!this->metricsPath.empty()) this->energies.push_back(this->computeEnergy());
 }
 

@@ -13,6 +13,9 @@
 //   MURB_B200_METRICS_CSV path: track the total energy after every iteration (what gpu+tracking does,
 //                         SimulationNBodyCUDAPropertyTracking.cu:217-369) and write it on destruction in the format of
 //                         SimulationHistory::saveMetricsToCSV (src/common/core/SimulationHistory.cpp:103-122)
+//   MURB_B200_HOST_MIRROR 1: copy positions and velocities back into the host SoA after every iteration.  The OpenGL
+//                         visualisers keep the raw host pointers they were given once (main.cpp:279-296) and read them
+//                         every frame, so this is what makes the tag usable without --nv (24 B/body per iteration)
 #ifndef SIMULATION_N_BODY_B200_HPP_
 #define SIMULATION_N_BODY_B200_HPP_
 
@@ -68,6 +71,7 @@ class SimulationNBodyB200 : public SimulationNBodyInterface<float> {
     int integrator; // B200NB_INTEGRATOR_*
     int nGpus;
     accSoA_t<float> accSoA;
+    bool hostMirror = false;       // refresh the host SoA after every iteration (visualiser hand-off)
     std::string metricsPath;       // empty: no tracking
     std::vector<double> energies;  // energies[i] = total energy after iteration i (fp64, like GPUSimulationHistory<double>)
 

@@ -247,6 +247,42 @@ TEST_CASE("gpu+b200 - metrics CSV", "[b200][metrics]")
 
 #ifdef USE_CUDA
 // Second comparator: the reference's own gpu+tile+full kernel recompiled for sm_100a, at a size cpu+naive cannot reach.
+// What createVisu does (main.cpp:279-296): take the raw host pointers once, read them after every iteration without
+// ever calling getDataSoA() again.  With MURB_B200_HOST_MIRROR=1 those pointers must show the current state.
+TEST_CASE("gpu+b200 - host mirror for the visualiser", "[b200][visu]")
+{
+    const size_t n = 3000;
+    setenv("MURB_B200_HOST_MIRROR", "1", 1);
+    B200BodiesAllocator b200Alloc(n, "galaxy");
+    SimulationNBodyB200 b200(b200Alloc, 2e8f);
+    unsetenv("MURB_B200_HOST_MIRROR");
+    BodiesAllocator<float> hostAlloc(n, "galaxy");
+    SimulationNBodyNaive<float> naive(hostAlloc, 2e8f);
+    b200.setDt(3600.f);
+    naive.setDt(3600.f);
+    const float *q[3] = {b200.getBodies()->getDataSoA().qx.data(), b200.getBodies()->getDataSoA().qy.data(),
+                         b200.getBodies()->getDataSoA().qz.data()};
+    const float *v[3] = {b200.getBodies()->getDataSoA().vx.data(), b200.getBodies()->getDataSoA().vy.data(),
+                         b200.getBodies()->getDataSoA().vz.data()};
+    const float *radius = b200.getBodies()->getDataSoA().r.data();
+    for (size_t it = 1; it <= 3; it++) {
+        b200.computeOneIteration();
+        naive.computeOneIteration();
+        const dataSoA_t<float> &g = naive.getBodies()->getDataSoA();
+        const std::vector<float> *gq[3] = {&g.qx, &g.qy, &g.qz};
+        const std::vector<float> *gv[3] = {&g.vx, &g.vy, &g.vz};
+        for (int axis = 0; axis < 3; axis++)
+            for (size_t body = 0; body < n; body++) {
+                CAPTURE(axis, body, it);
+                REQUIRE_THAT(q[axis][body], Catch::Matchers::WithinRel((*gq[axis])[body], 1e-4f) ||
+                                                Catch::Matchers::WithinAbs((*gq[axis])[body], 1.f));
+                REQUIRE_THAT(v[axis][body], Catch::Matchers::WithinRel((*gv[axis])[body], 1e-3f) ||
+                                                Catch::Matchers::WithinAbs((*gv[axis])[body], 1e-3f));
+            }
+        REQUIRE(radius[n - 1] == g.r[n - 1]);
+    }
+}
+
 TEST_CASE("gpu+b200 vs reference gpu+tile+full", "[b200][tilefull]")
 {
     const size_t n = 50001, nIte = 3;
