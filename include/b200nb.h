@@ -101,6 +101,23 @@ int b200nb_integrate_host_accel(b200nb_ctx *ctx, const float *ax, const float *a
  * self term the same way.  Joins the devices.  Collective when n_ranks > 1. */
 int b200nb_energy(b200nb_ctx *ctx, double *total);
 
+/* Every per-iteration metric of the reference's history in one pass (SimulationHistory.hpp:12-15; CSV columns
+ * "iteration,energy,ang_momentum,density_center_x,density_center_y,density_center_z", SimulationHistory.hpp:45 and
+ * SimulationHistory.cpp:103-122).  Upstream only ever fills in the energy (SimulationNBodyCUDAPropertyTracking.cu:
+ * 217-304); the angular momentum and density centre are declared and exported but never computed, so their
+ * definitions are fixed here:  L = sum_i m_i (r_i x v_i) about the origin (ang_momentum = |L|);  centre of mass;
+ * density centre = sum_i w_i r_i / sum_i w_i with w_i = m_i * sum_{j != i} G m_j / sqrt(|r_ij|^2 + soft^2), the
+ * potential-weighted centre.  out[B200NB_N_METRICS], fp64.  Joins the devices.  Collective when n_ranks > 1. */
+enum {
+    B200NB_METRIC_ENERGY = 0,
+    B200NB_METRIC_ANG_X = 1, B200NB_METRIC_ANG_Y = 2, B200NB_METRIC_ANG_Z = 3,
+    B200NB_METRIC_MASS = 4,
+    B200NB_METRIC_COM_X = 5, B200NB_METRIC_COM_Y = 6, B200NB_METRIC_COM_Z = 7,
+    B200NB_METRIC_DENSITY_X = 8, B200NB_METRIC_DENSITY_Y = 9, B200NB_METRIC_DENSITY_Z = 10,
+    B200NB_N_METRICS = 11
+};
+int b200nb_metrics(b200nb_ctx *ctx, double *out);
+
 /* Joins every device and communication stream.  main.cpp:353-371 only synchronises the current device, so the glue
  * calls this when more than one device is in use. */
 int b200nb_sync(b200nb_ctx *ctx);

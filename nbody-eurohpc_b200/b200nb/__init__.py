@@ -73,6 +73,7 @@ def lib() -> ctypes.CDLL:
         "b200nb_accel": (c_int, [ctx]),
         "b200nb_integrate_host_accel": (c_int, [ctx, _FP, _FP, _FP, c_float]),
         "b200nb_energy": (c_int, [ctx, POINTER(c_double)]),
+        "b200nb_metrics": (c_int, [ctx, POINTER(c_double)]),
         "b200nb_sync": (c_int, [ctx]),
         "b200nb_n_bodies": (c_uint64, [ctx]),
         "b200nb_n_local_gpus": (c_int, [ctx]),
@@ -253,6 +254,14 @@ class Context:
         e = c_double()
         self._check(self._L.b200nb_energy(self._ctx, byref(e)), "b200nb_energy")
         return e.value
+
+    METRIC_NAMES = ("energy", "ang_x", "ang_y", "ang_z", "mass", "com_x", "com_y", "com_z", "density_x", "density_y", "density_z")
+
+    def metrics(self) -> dict:
+        """energy, angular momentum vector, total mass, centre of mass, density centre (include/b200nb.h: b200nb_metrics)."""
+        out = (c_double * len(self.METRIC_NAMES))()
+        self._check(self._L.b200nb_metrics(self._ctx, out), "b200nb_metrics")
+        return dict(zip(self.METRIC_NAMES, list(out)))
 
     def sync(self):
         self._check(self._L.b200nb_sync(self._ctx), "b200nb_sync")

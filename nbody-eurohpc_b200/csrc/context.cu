@@ -219,8 +219,8 @@ int alloc_buffers(b200nb_ctx *c, Shard &s)
     CU(c, dmalloc((void **)&s.partial, (size_t)c->rows * 3 * L * 4));
     CU(c, dmalloc((void **)&s.stage, 7 * c->stage_stride * 4));
     const size_t eb = (L + ENERGY_THREADS - 1) / ENERGY_THREADS;
-    CU(c, dmalloc((void **)&s.energy_blocks, eb * 8));
-    CU(c, dmalloc((void **)&s.energy_out, 8));
+    CU(c, dmalloc((void **)&s.energy_blocks, eb * 8 * MR_COUNT));
+    CU(c, dmalloc((void **)&s.energy_out, 8 * MR_COUNT));
     CU(c, cudaMemsetAsync(s.acc, 0, 3 * L * 4, s.s_compute));
     CU(c, cudaMemsetAsync(s.vel, 0, 3 * L * 4, s.s_compute));
     CU(c, cudaEventRecord(s.ev_gathered, s.s_comm)); // "positions are current" before the first step
@@ -803,34 +803,59 @@ int b200nb_integrate_host_accel(b200nb_ctx *c, const float *ax, const float *ay,
     return sync_all(c); // borrowed host pointers (see upload)
 }
 
-int b200nb_energy(b200nb_ctx *c, double *total)
+// raw[MR_COUNT]: the metric rows summed over every body of every rank
+static int metric_sums(b200nb_ctx *c, double *raw)
 {
-    if (!c || !total) return B200NB_EINVAL;
-    if (!c->uploaded) return fail(c, B200NB_ESTATE, "energy before upload");
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "metrics before upload");
     DeviceGuard guard;
     if (int rc = sync_all(c)) return rc; // positions gathered, velocities final
-    double sum = 0.0;
+    for (int k = 0; k < MR_COUNT; ++k) raw[k] = 0.0;
     for (auto &s : c->shards) {
         CU(c, cudaSetDevice(s.device));
         const uint32_t nb = (s.n_local + ENERGY_THREADS - 1) / ENERGY_THREADS;
-        double e = 0.0;
+        double part[MR_COUNT];
         if (nb > 0) {
             energy_kernel<<<nb, ENERGY_THREADS, 0, s.s_compute>>>(s.bodies, s.vel, s.mass, (uint32_t)c->L, s.n_local,
                                                                  (uint64_t)s.rank * c->L, c->nblk_total, c->soft2,
                                                                  s.energy_blocks);
-            energy_final_kernel<<<1, 256, 0, s.s_compute>>>(s.energy_blocks, nb, s.energy_out);
+            energy_final_kernel<<<MR_COUNT, 256, 0, s.s_compute>>>(s.energy_blocks, nb, s.energy_out);
             c->launches += 2;
             CU(c, cudaGetLastError());
         } else {
-            CU(c, cudaMemsetAsync(s.energy_out, 0, 8, s.s_compute));
+            CU(c, cudaMemsetAsync(s.energy_out, 0, 8 * MR_COUNT, s.s_compute));
         }
         if (c->shards.size() != (size_t)c->n_ranks) // one rank per process: sum over ranks on the device
-            NC(c, g_nccl.AllReduce(s.energy_out, s.energy_out, 1, ncclDouble, ncclSum, s.comm, s.s_compute));
-        CU(c, cudaMemcpyAsync(&e, s.energy_out, 8, cudaMemcpyDeviceToHost, s.s_compute));
+            NC(c, g_nccl.AllReduce(s.energy_out, s.energy_out, MR_COUNT, ncclDouble, ncclSum, s.comm, s.s_compute));
+        CU(c, cudaMemcpyAsync(part, s.energy_out, 8 * MR_COUNT, cudaMemcpyDeviceToHost, s.s_compute));
         CU(c, cudaStreamSynchronize(s.s_compute));
-        sum += e;
+        for (int k = 0; k < MR_COUNT; ++k) raw[k] += part[k];
     }
-    *total = sum;
+    return B200NB_OK;
+}
+
+int b200nb_energy(b200nb_ctx *c, double *total)
+{
+    if (!c || !total) return B200NB_EINVAL;
+    double raw[MR_COUNT];
+    if (int rc = metric_sums(c, raw)) return rc;
+    *total = raw[MR_ENERGY];
+    return B200NB_OK;
+}
+
+int b200nb_metrics(b200nb_ctx *c, double *out)
+{
+    if (!c || !out) return B200NB_EINVAL;
+    double raw[MR_COUNT];
+    if (int rc = metric_sums(c, raw)) return rc;
+    out[B200NB_METRIC_ENERGY] = raw[MR_ENERGY];
+    out[B200NB_METRIC_ANG_X] = raw[MR_LX];
+    out[B200NB_METRIC_ANG_Y] = raw[MR_LY];
+    out[B200NB_METRIC_ANG_Z] = raw[MR_LZ];
+    out[B200NB_METRIC_MASS] = raw[MR_M];
+    for (int k = 0; k < 3; ++k) {
+        out[B200NB_METRIC_COM_X + k] = raw[MR_M] != 0.0 ? raw[MR_MX + k] / raw[MR_M] : 0.0;
+        out[B200NB_METRIC_DENSITY_X + k] = raw[MR_W] != 0.0 ? raw[MR_WX + k] / raw[MR_W] : out[B200NB_METRIC_COM_X + k];
+    }
     return B200NB_OK;
 }
 

@@ -160,10 +160,19 @@ __global__ void __launch_bounds__(256) load_acc_kernel(const float *__restrict__
     acc[2 * L + i] = stage[2 * stride + first + i];
 }
 
-// ---------------------------------------------------------------------------------------------- energy
-// E_i = m_i |v_i|^2 / 2  -  (m_i / 2) * ( sum_j Gm_j / sqrt(r_ij^2 + soft^2)  -  Gm_i / soft )
-// (definition and self-term handling: SimulationNBodyCUDAPropertyTracking.cu:262-301).  The pair sum uses
-// rsqrt.approx + one Newton step (~1e-7 relative), 128-term fp32 tile sums and an fp64 running sum.
+// ---------------------------------------------------------------------------------------------- metrics
+// One pass produces every per-iteration metric of the reference's history (SimulationHistory.hpp:12-15, CSV columns
+// :45): the total energy (the only one computed upstream), and the angular momentum and density centre that are
+// declared there but never filled in.
+//   E_i = m_i |v_i|^2 / 2  -  (m_i / 2) * ( sum_j Gm_j / sqrt(r_ij^2 + soft^2)  -  Gm_i / soft )
+//         (definition and self-term handling: SimulationNBodyCUDAPropertyTracking.cu:262-301)
+//   L   = sum_i m_i (r_i x v_i)                                  about the origin
+//   centre of mass   = sum_i m_i r_i / sum_i m_i
+//   density centre   = sum_i w_i r_i / sum_i w_i,  w_i = m_i * (softened potential at body i, self term excluded):
+//                      the potential-weighted centre, which follows the densest region instead of the mass mean
+// The pair sum uses rsqrt.approx + one Newton step (~1e-7 relative), 128-term fp32 tile sums and an fp64 running sum;
+// everything per-body is fp64.  Rows of the raw output (summed over blocks, then over ranks, by the caller):
+enum MetricRow { MR_ENERGY = 0, MR_LX, MR_LY, MR_LZ, MR_M, MR_MX, MR_MY, MR_MZ, MR_W, MR_WX, MR_WY, MR_WZ, MR_COUNT };
 constexpr int ENERGY_THREADS = 128;
 
 __device__ __forceinline__ float rsqrt_nr(float d)
@@ -172,6 +181,7 @@ __device__ __forceinline__ float rsqrt_nr(float d)
     return y * fmaf(-0.5f * d, y * y, 1.5f);
 }
 
+// block_out[row * n_blocks + block]
 __global__ void __launch_bounds__(ENERGY_THREADS) energy_kernel(const float *__restrict__ bodies,
                                                                 const float *__restrict__ vel,
                                                                 const float *__restrict__ mass, uint32_t L,
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(ENERGY_THREADS) energy_kernel(const float *__r
                                                                 float soft2, double *__restrict__ block_out)
 {
     __shared__ __align__(16) float tile[BLK_FLOATS];
-    __shared__ double warp_sums[ENERGY_THREADS / 32];
+    __shared__ double warp_sums[MR_COUNT][ENERGY_THREADS / 32];
     const uint32_t i = blockIdx.x * ENERGY_THREADS + threadIdx.x;
     const bool valid = i < n_local;
     const size_t g = first + (valid ? i : 0);
@@ -201,39 +211,52 @@ __global__ void __launch_bounds__(ENERGY_THREADS) energy_kernel(const float *__r
         }
         pot += (double)s;
     }
-    double e = 0.0;
+    double r[MR_COUNT];
+#pragma unroll
+    for (int k = 0; k < MR_COUNT; ++k) r[k] = 0.0;
     if (valid) {
-        const float vx = vel[i], vy = vel[L + i], vz = vel[2 * (size_t)L + i];
+        const double vx = vel[i], vy = vel[L + i], vz = vel[2 * (size_t)L + i];
+        const double x = xi, y = yi, z = zi;
         const double m = (double)mass[i];
         const double self = (double)gi * (double)rsqrt_nr(soft2);
-        const double v2 = (double)vx * vx + (double)vy * vy + (double)vz * vz;
-        e = 0.5 * m * v2 - 0.5 * m * (pot - self);
+        const double v2 = vx * vx + vy * vy + vz * vz;
+        const double w = m * (pot - self);
+        r[MR_ENERGY] = 0.5 * m * v2 - 0.5 * w;
+        r[MR_LX] = m * (y * vz - z * vy);
+        r[MR_LY] = m * (z * vx - x * vz);
+        r[MR_LZ] = m * (x * vy - y * vx);
+        r[MR_M] = m;  r[MR_MX] = m * x; r[MR_MY] = m * y; r[MR_MZ] = m * z;
+        r[MR_W] = w;  r[MR_WX] = w * x; r[MR_WY] = w * y; r[MR_WZ] = w * z;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = e;
+    for (int k = 0; k < MR_COUNT; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r[k] += __shfl_down_sync(0xffffffffu, r[k], o);
+        if ((threadIdx.x & 31) == 0) warp_sums[k][threadIdx.x >> 5] = r[k];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < MR_COUNT) {
         double t = 0.0;
-        for (int w = 0; w < ENERGY_THREADS / 32; ++w) t += warp_sums[w];
-        block_out[blockIdx.x] = t;
+        for (int w = 0; w < ENERGY_THREADS / 32; ++w) t += warp_sums[threadIdx.x][w];
+        block_out[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
     }
 }
 
-// fixed-order final sum (deterministic; replaces cub::DeviceReduce::Sum and its per-call cudaMalloc)
+// fixed-order final sum, one block per row (deterministic; replaces cub::DeviceReduce::Sum and its per-call cudaMalloc)
 __global__ void __launch_bounds__(256) energy_final_kernel(const double *__restrict__ block_out, uint32_t nb,
                                                           double *__restrict__ out)
 {
     __shared__ double sh[256];
+    const double *row = block_out + (size_t)blockIdx.x * nb;
     double t = 0.0;
-    for (uint32_t k = threadIdx.x; k < nb; k += 256) t += block_out[k];
+    for (uint32_t k = threadIdx.x; k < nb; k += 256) t += row[k];
     sh[threadIdx.x] = t;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = sh[0];
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
 } // namespace b200nb

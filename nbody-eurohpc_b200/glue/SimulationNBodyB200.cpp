@@ -1,5 +1,6 @@
 #include "SimulationNBodyB200.hpp"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -147,8 +148,8 @@ SimulationNBodyB200::~SimulationNBodyB200()
 
 void SimulationNBodyB200::saveMetricsToCSV(const std::string &filePath) const
 {
-    // same columns as SimulationHistory<T>::saveMetricsToCSV; angular momentum and density centre are declared but
-    // never computed upstream (they stay 0 there too)
+    // same columns as SimulationHistory<T>::saveMetricsToCSV (SimulationHistory.cpp:103-122).  Upstream only ever fills
+    // in the energy; |L| and the density centre are computed here with the definitions of include/b200nb.h
     std::ofstream out(filePath);
     if (!out.is_open()) {
         std::fprintf(stderr, "gpu+b200: cannot open metrics file '%s'\n", filePath.c_str());
@@ -156,7 +157,9 @@ void SimulationNBodyB200::saveMetricsToCSV(const std::string &filePath) const
     }
     out << "iteration,energy,ang_momentum,density_center_x,density_center_y,density_center_z\n";
     out << std::setprecision(std::numeric_limits<double>::max_digits10);
-    for (size_t i = 0; i < this->energies.size(); i++) out << i << ',' << this->energies[i] << ",0,0,0,0\n";
+    for (size_t i = 0; i < this->energies.size(); i++)
+        out << i << ',' << this->energies[i] << ',' << this->angMomentums[i] << ',' << this->densityCenters[i][0] << ','
+            << this->densityCenters[i][1] << ',' << this->densityCenters[i][2] << '\n';
 }
 
 void SimulationNBodyB200::computeOneIteration()
@@ -167,7 +170,25 @@ void SimulationNBodyB200::computeOneIteration()
     if (b200nb_n_local_gpus(c) > 1) check(b200nb_sync(c), c, "b200nb_sync");
     this->b200Bodies->invalidateDataSoA();
     if (this->hostMirror) (void)this->b200Bodies->getDataSoA(); // in place: the vectors never move, captured pointers stay valid
-    if (!this->metricsPath.empty()) this->energies.push_back(this->computeEnergy());
+    if (!this->metricsPath.empty()) this->recordMetrics();
+}
+
+void SimulationNBodyB200::recordMetrics()
+{
+    const std::array<double, B200NB_N_METRICS> m = this->computeMetrics();
+    this->energies.push_back(m[B200NB_METRIC_ENERGY]);
+    this->angMomentums.push_back(std::sqrt(m[B200NB_METRIC_ANG_X] * m[B200NB_METRIC_ANG_X] +
+                                           m[B200NB_METRIC_ANG_Y] * m[B200NB_METRIC_ANG_Y] +
+                                           m[B200NB_METRIC_ANG_Z] * m[B200NB_METRIC_ANG_Z]));
+    this->densityCenters.push_back({m[B200NB_METRIC_DENSITY_X], m[B200NB_METRIC_DENSITY_Y], m[B200NB_METRIC_DENSITY_Z]});
+}
+
+std::array<double, B200NB_N_METRICS> SimulationNBodyB200::computeMetrics()
+{
+    b200nb_ctx *c = this->b200Bodies->context();
+    std::array<double, B200NB_N_METRICS> m{};
+    check(b200nb_metrics(c, m.data()), c, "b200nb_metrics");
+    return m;
 }
 
 void SimulationNBodyB200::computeAccelerationsOnly()

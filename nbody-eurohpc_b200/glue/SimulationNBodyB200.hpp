@@ -10,8 +10,9 @@
 // Environment (precedent: MURB_HETERO_GPU_FRACTION / MURB_HETERO_MIN_N, SimulationNBodyHetero.cu:217-227):
 //   MURB_B200_NGPUS       number of GPUs to shard the targets over (default 1; 0 = all visible)
 //   MURB_B200_INTEGRATOR  "murb" (default) or "leapfrog"; the tag gpu+b200+leapfrog selects leapfrog too
-//   MURB_B200_METRICS_CSV path: track the total energy after every iteration (what gpu+tracking does,
-//                         SimulationNBodyCUDAPropertyTracking.cu:217-369) and write it on destruction in the format of
+//   MURB_B200_METRICS_CSV path: track the total energy (what gpu+tracking does,
+//                         SimulationNBodyCUDAPropertyTracking.cu:217-369), |angular momentum| and the density centre
+//                         after every iteration and write them on destruction in the format of
 //                         SimulationHistory::saveMetricsToCSV (src/common/core/SimulationHistory.cpp:103-122)
 //   MURB_B200_HOST_MIRROR 1: copy positions and velocities back into the host SoA after every iteration.  The OpenGL
 //                         visualisers keep the raw host pointers they were given once (main.cpp:279-296) and read them
@@ -19,6 +20,7 @@
 #ifndef SIMULATION_N_BODY_B200_HPP_
 #define SIMULATION_N_BODY_B200_HPP_
 
+#include <array>
 #include <memory>
 #include <string>
 #include <vector>
@@ -27,7 +29,7 @@
 #include "core/BodiesAllocator.hpp"
 #include "core/SimulationNBodyInterface.hpp"
 
-struct b200nb_ctx;
+#include "b200nb.h"
 
 class B200Bodies : public Bodies<float> {
   protected:
@@ -74,6 +76,9 @@ class SimulationNBodyB200 : public SimulationNBodyInterface<float> {
     bool hostMirror = false;       // refresh the host SoA after every iteration (visualiser hand-off)
     std::string metricsPath;       // empty: no tracking
     std::vector<double> energies;  // energies[i] = total energy after iteration i (fp64, like GPUSimulationHistory<double>)
+    std::vector<double> angMomentums;                  // |L| after iteration i (SimulationHistory.hpp:14)
+    std::vector<std::array<double, 3>> densityCenters; // SimulationHistory.hpp:15
+    void recordMetrics();
 
   public:
     SimulationNBodyB200(const BodiesAllocatorInterface<float> &allocator, const float soft = 0.035f,
@@ -84,7 +89,10 @@ class SimulationNBodyB200 : public SimulationNBodyInterface<float> {
     void computeAccelerationsOnly();    // force pass without integration (accuracy tests)
     double computeEnergy();             // fp64 total energy (…PropertyTracking.cu:217-304 definition)
     const char *kernelName() const;
+    std::array<double, B200NB_N_METRICS> computeMetrics(); // indices: B200NB_METRIC_* (include/b200nb.h)
     const std::vector<double> &getEnergies() const { return energies; }
+    const std::vector<double> &getAllAngMomentum() const { return angMomentums; }
+    const std::vector<std::array<double, 3>> &getAllDensityCenter() const { return densityCenters; }
     void saveMetricsToCSV(const std::string &filePath) const;
 };
 

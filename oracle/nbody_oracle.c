@@ -194,3 +194,30 @@ double oracle_energy_f64(uint64_t n, const float *qx, const float *qy, const flo
     }
     return total;
 }
+
+void oracle_metrics_f64(uint64_t n, const float *qx, const float *qy, const float *qz, const float *vx, const float *vy,
+                        const float *vz, const float *m, float G, float soft, double *out)
+{
+    const double Gd = (double)G, s2 = (double)soft * (double)soft;
+    double e = 0, lx = 0, ly = 0, lz = 0, M = 0, mx = 0, my = 0, mz = 0, W = 0, wx = 0, wy = 0, wz = 0;
+#pragma omp parallel for schedule(static) reduction(+ : e, lx, ly, lz, M, mx, my, mz, W, wx, wy, wz)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const double xi = qx[i], yi = qy[i], zi = qz[i], mi = m[i], ui = vx[i], vi = vy[i], wi = vz[i];
+        double pot = 0.0;
+        for (uint64_t j = 0; j < n; j++) {
+            if ((uint64_t)i == j) continue;
+            const double rx = (double)qx[j] - xi, ry = (double)qy[j] - yi, rz = (double)qz[j] - zi;
+            pot += Gd * (double)m[j] / sqrt(rx * rx + ry * ry + rz * rz + s2);
+        }
+        const double w = mi * pot;
+        e += 0.5 * mi * (ui * ui + vi * vi + wi * wi) - 0.5 * w;
+        lx += mi * (yi * wi - zi * vi);
+        ly += mi * (zi * ui - xi * wi);
+        lz += mi * (xi * vi - yi * ui);
+        M += mi; mx += mi * xi; my += mi * yi; mz += mi * zi;
+        W += w; wx += w * xi; wy += w * yi; wz += w * zi;
+    }
+    out[0] = e; out[1] = lx; out[2] = ly; out[3] = lz; out[4] = M;
+    out[5] = M != 0 ? mx / M : 0; out[6] = M != 0 ? my / M : 0; out[7] = M != 0 ? mz / M : 0;
+    out[8] = W != 0 ? wx / W : out[5]; out[9] = W != 0 ? wy / W : out[6]; out[10] = W != 0 ? wz / W : out[7];
+}

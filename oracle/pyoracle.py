@@ -47,6 +47,8 @@ class Oracle:
         L.oracle_run_f64force.restype = None
         L.oracle_energy_f64.argtypes = [u64] + [FP] * 7 + [f, f]
         L.oracle_energy_f64.restype = ctypes.c_double
+        L.oracle_metrics_f64.argtypes = [u64] + [FP] * 7 + [f, f, ctypes.POINTER(ctypes.c_double)]
+        L.oracle_metrics_f64.restype = None
         self.L = L
 
     def init_bodies(self, scheme, n, seed=0):
@@ -90,6 +92,14 @@ class Oracle:
     def energy(self, d, G=G_F32, soft=SOFT):
         n = len(d["qx"])
         return self.L.oracle_energy_f64(n, *[_fp(d[k]) for k in ("qx", "qy", "qz", "vx", "vy", "vz", "m")], G, soft)
+
+    METRIC_NAMES = ("energy", "ang_x", "ang_y", "ang_z", "mass", "com_x", "com_y", "com_z", "density_x", "density_y", "density_z")
+
+    def metrics(self, d, G=G_F32, soft=SOFT):
+        n = len(d["qx"])
+        out = (ctypes.c_double * 11)()
+        self.L.oracle_metrics_f64(n, *[_fp(d[k]) for k in ("qx", "qy", "qz", "vx", "vy", "vz", "m")], G, soft, out)
+        return dict(zip(self.METRIC_NAMES, list(out)))
 
 
 def max_rel_err(ref3, got3):

@@ -233,6 +233,17 @@ TEST_CASE("gpu+b200 - metrics CSV", "[b200][metrics]")
         for (int it = 0; it < 5; it++) simu.computeOneIteration();
         REQUIRE(simu.getEnergies().size() == 5);
         for (double e : simu.getEnergies()) REQUIRE(std::abs((e - e0) / e0) < 1e-4);
+        // the columns upstream leaves empty: |L| is conserved by kick-drift-kick (central pairwise forces), and the
+        // potential-weighted centre of the galaxy scheme sits on the 2e24 kg body at the origin
+        REQUIRE(simu.getAllAngMomentum().size() == 5);
+        const double l0 = simu.getAllAngMomentum()[0];
+        REQUIRE(l0 > 0);
+        for (double l : simu.getAllAngMomentum()) REQUIRE(std::abs((l - l0) / l0) < 1e-5);
+        for (const auto &dc : simu.getAllDensityCenter())
+            for (int axis = 0; axis < 3; axis++) REQUIRE(std::abs(dc[axis]) < 2e7); // bodies live at 1e8..2e8 m
+        const auto m = simu.computeMetrics();
+        REQUIRE(m[B200NB_METRIC_ENERGY] == simu.getEnergies().back());
+        REQUIRE(m[B200NB_METRIC_MASS] > 2e24);
     } // destructor writes the file
     unsetenv("MURB_B200_METRICS_CSV");
     std::ifstream in(path);
@@ -241,12 +252,17 @@ TEST_CASE("gpu+b200 - metrics CSV", "[b200][metrics]")
     std::getline(in, line);
     REQUIRE(line == "iteration,energy,ang_momentum,density_center_x,density_center_y,density_center_z");
     int rows = 0;
-    while (std::getline(in, line)) if (!line.empty()) rows++;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        rows++;
+        int commas = 0;
+        for (char ch : line) commas += ch == ',';
+        REQUIRE(commas == 5);
+        REQUIRE(line.find(",0,0,0,0") == std::string::npos); // the last four columns carry values now
+    }
     REQUIRE(rows == 5);
 }
 
-#ifdef USE_CUDA
-// Second comparator: the reference's own gpu+tile+full kernel recompiled for sm_100a, at a size cpu+naive cannot reach.
 // What createVisu does (main.cpp:279-296): take the raw host pointers once, read them after every iteration without
 // ever calling getDataSoA() again.  With MURB_B200_HOST_MIRROR=1 those pointers must show the current state.
 TEST_CASE("gpu+b200 - host mirror for the visualiser", "[b200][visu]")
@@ -283,6 +299,8 @@ TEST_CASE("gpu+b200 - host mirror for the visualiser", "[b200][visu]")
     }
 }
 
+#ifdef USE_CUDA
+// Second comparator: the reference's own gpu+tile+full kernel recompiled for sm_100a, at a size cpu+naive cannot reach.
 TEST_CASE("gpu+b200 vs reference gpu+tile+full", "[b200][tilefull]")
 {
     const size_t n = 50001, nIte = 3;

@@ -30,12 +30,13 @@ def main():
             state = ctx.download_state()      # collective
             acc = ctx.download_accel()        # collective
             energy = ctx.energy()             # collective
+            metrics = ctx.metrics()           # collective (12-row all-reduce)
             ctx.close()
             if rank == 0:
                 with b200nb.Context(n, b200nb.G_F32, SOFT, rank=0, n_ranks=1, device=local_rank) as one:
                     one.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
                     one.step(DT, integ, 4)
-                    s1, a1, e1 = one.download_state(), one.download_accel(), one.energy()
+                    s1, a1, e1, m1 = one.download_state(), one.download_accel(), one.energy(), one.metrics()
                 scale = max(float(np.abs(s1[c]).max()) for c in ("qx", "qy", "qz"))
                 for c in ("qx", "qy", "qz"):
                     ok &= bool(np.all(np.abs(state[c].astype(np.float64) - s1[c]) <= 1e-6 * scale))
@@ -45,6 +46,10 @@ def main():
                 den = np.linalg.norm(np.stack(a1).astype(np.float64), axis=0)
                 ok &= bool(np.max(num / den) <= 2e-6)
                 ok &= abs(energy - e1) <= 1e-6 * abs(e1)
+                l1 = float(np.linalg.norm([m1[k] for k in ("ang_x", "ang_y", "ang_z")]))
+                ok &= all(abs(metrics[k] - m1[k]) <= 1e-5 * l1 for k in ("ang_x", "ang_y", "ang_z"))
+                ok &= all(abs(metrics[k] - m1[k]) <= 1e-5 * scale for k in ("com_x", "com_y", "com_z", "density_x", "density_y", "density_z"))
+                ok &= abs(metrics["mass"] - m1["mass"]) <= 1e-12 * m1["mass"]
                 print(f"n={n} {scheme} integrator={integ}: max|da|/|a| {np.max(num / den):.2e}, dE {abs(energy - e1) / abs(e1):.1e}, ok={ok}", flush=True)
     # large N, where only sampled targets can be checked on the CPU: fp64 all-pairs oracle (tests/conftest.py)
     import importlib.util

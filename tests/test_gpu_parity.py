@@ -279,6 +279,34 @@ def _n_devices():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("scheme,n", [("galaxy", 4096), ("random", 3001)])
+def test_metrics_match_oracle_and_leapfrog_conserves_angular_momentum(b200, oracle, scheme, n):
+    """b200nb_metrics: the columns of the reference's metrics CSV (SimulationHistory.hpp:45).  Energy has an upstream
+    definition; |L| and the density centre do not (declared, never computed), so the oracle restates include/b200nb.h."""
+    d = oracle.init_bodies(scheme, n)
+    ref = oracle.metrics(d)
+    assert abs(ref["energy"] - oracle.energy(d)) <= 1e-12 * abs(ref["energy"])
+    box = max(float(np.abs(d[c]).max()) for c in ("qx", "qy", "qz"))
+    lnorm = float(np.linalg.norm([ref["ang_x"], ref["ang_y"], ref["ang_z"]]))
+    with make_ctx(b200, d) as ctx:
+        got = ctx.metrics()
+        assert got["energy"] == ctx.energy()
+        assert abs(got["energy"] - ref["energy"]) <= 1e-6 * abs(ref["energy"])
+        assert abs(got["mass"] - ref["mass"]) <= 1e-12 * ref["mass"]
+        for k in ("ang_x", "ang_y", "ang_z"):  # fp64 sums of exactly representable fp32 products
+            assert abs(got[k] - ref[k]) <= 1e-10 * lnorm, k
+        for k in ("com_x", "com_y", "com_z"):
+            assert abs(got[k] - ref[k]) <= 1e-10 * box, k
+        for k in ("density_x", "density_y", "density_z"):  # weights carry the fp32 potential (rsqrt + NR, ~1e-7)
+            assert abs(got[k] - ref[k]) <= 1e-6 * box, k
+        # kick-drift-kick with central pair forces conserves L up to fp32 rounding of the state
+        ctx.step(DT, 1, 200)
+        after = ctx.metrics()
+        l1 = float(np.linalg.norm([after["ang_x"], after["ang_y"], after["ang_z"]]))
+        assert abs(l1 - lnorm) <= 2e-5 * lnorm
+        assert abs(after["mass"] - ref["mass"]) <= 1e-12 * ref["mass"]
+
+
 @pytest.mark.parametrize("integrator", [0, 1])
 def test_two_gpus_match_one(b200, oracle, integrator):
     if _n_devices() < 2:
@@ -289,7 +317,7 @@ def test_two_gpus_match_one(b200, oracle, integrator):
     for g in (1, 2):
         with make_ctx(b200, d, n_gpus=g) as ctx:
             ctx.step(DT, integrator, 5)
-            outs.append((ctx.download_state(), ctx.download_accel(), ctx.energy()))
+            outs.append((ctx.download_state(), ctx.download_accel(), ctx.energy(), ctx.metrics()))
     # different chunking => different (fixed) summation order: agreement to a few fp32 ulps of the system size
     # (absolute bound: the central body sits at the origin, where a relative bound is meaningless)
     scale = max(float(np.abs(outs[0][0][c]).max()) for c in ("qx", "qy", "qz"))
@@ -297,6 +325,11 @@ def test_two_gpus_match_one(b200, oracle, integrator):
         assert np.all(np.abs(outs[0][0][c].astype(np.float64) - outs[1][0][c]) <= 1e-6 * scale), c
     assert max_rel_err(outs[0][1], outs[1][1]) <= 2e-6
     assert abs(outs[0][2] - outs[1][2]) <= 1e-6 * abs(outs[0][2])
+    l0 = float(np.linalg.norm([outs[0][3][k] for k in ("ang_x", "ang_y", "ang_z")]))
+    for k in ("ang_x", "ang_y", "ang_z"):
+        assert abs(outs[0][3][k] - outs[1][3][k]) <= 1e-5 * l0, k
+    for k in ("density_x", "density_y", "density_z", "com_x", "com_y", "com_z"):
+        assert abs(outs[0][3][k] - outs[1][3][k]) <= 1e-5 * scale, k
 
 
 def test_torchrun_ranks_match_single_gpu():

@@ -77,3 +77,29 @@ def test_energy_and_leapfrog(oracle):
     p = [float(np.sum(d0["m"].astype(np.float64) * a[k])) for k in range(3)]
     scale = float(np.sum(d0["m"].astype(np.float64) * np.linalg.norm(np.stack(a), axis=0)))
     assert max(abs(x) for x in p) < 1e-9 * scale
+
+
+def test_metrics_restatement_is_self_consistent(oracle):
+    """oracle_metrics_f64 against numpy on a size numpy handles: energy equals oracle_energy_f64 (the upstream-defined
+    metric), L / centre of mass / potential-weighted centre equal their textbook formulas."""
+    n = 700
+    d = oracle.init_bodies("random", n)
+    m = oracle.metrics(d)
+    assert abs(m["energy"] - oracle.energy(d)) <= 1e-12 * abs(m["energy"])
+    q = np.stack([d[c].astype(np.float64) for c in ("qx", "qy", "qz")], 1)
+    v = np.stack([d[c].astype(np.float64) for c in ("vx", "vy", "vz")], 1)
+    mass = d["m"].astype(np.float64)
+    L = (mass[:, None] * np.cross(q, v)).sum(0)
+    com = (mass[:, None] * q).sum(0) / mass.sum()
+    G, soft = float(np.float32(6.67384e-11)), 2e8
+    r2 = ((q[:, None, :] - q[None, :, :]) ** 2).sum(-1) + soft * soft
+    inv = 1.0 / np.sqrt(r2)
+    np.fill_diagonal(inv, 0.0)
+    w = mass * (inv @ (G * mass))
+    dc = (w[:, None] * q).sum(0) / w.sum()
+    got_L = np.array([m["ang_x"], m["ang_y"], m["ang_z"]])
+    assert np.all(np.abs(got_L - L) <= 1e-11 * np.linalg.norm(L))
+    assert abs(m["mass"] - mass.sum()) <= 1e-13 * mass.sum()
+    box = np.abs(q).max()
+    assert np.all(np.abs(np.array([m["com_x"], m["com_y"], m["com_z"]]) - com) <= 1e-11 * box)
+    assert np.all(np.abs(np.array([m["density_x"], m["density_y"], m["density_z"]]) - dc) <= 1e-11 * box)
