@@ -247,6 +247,34 @@ __device__ __forceinline__ void block_packed(const float *__restrict__ sb, const
     }
 }
 
+// The same block with the sources broadcast by warp shuffles instead of same-address shared-memory loads: every lane
+// keeps one source of a 32-source group in registers (one conflict-free LDS per component) and each source pair costs
+// 8 SHFL.IDX where block_packed needs 2 LDS.128.  Comparator only (MATH = 3): the arithmetic is identical, the
+// shuffles add issue slots and 4 live registers and buy nothing, see profiles/r01_shuffle_vs_lds.txt.
+template <int R>
+__device__ __forceinline__ void block_packed_shfl(const float *__restrict__ sb, const float (&xi)[R], const float (&yi)[R],
+                                                  const float (&zi)[R], uint64_t soft2p, uint64_t (&ax)[R],
+                                                  uint64_t (&ay)[R], uint64_t (&az)[R])
+{
+    const int lane = threadIdx.x & 31;
+    for (int g = 0; g < BLK; g += 32) {
+        const float xr = sb[g + lane], yr = sb[BLK + g + lane], zr = sb[2 * BLK + g + lane], gr = sb[3 * BLK + g + lane];
+#pragma unroll 2
+        for (int j = 0; j < 32; j += 2) {
+            const uint64_t sj[3] = {pk2(__shfl_sync(0xffffffffu, xr, j), __shfl_sync(0xffffffffu, xr, j + 1)),
+                                    pk2(__shfl_sync(0xffffffffu, yr, j), __shfl_sync(0xffffffffu, yr, j + 1)),
+                                    pk2(__shfl_sync(0xffffffffu, zr, j), __shfl_sync(0xffffffffu, zr, j + 1))};
+            const uint64_t gj = pk2(__shfl_sync(0xffffffffu, gr, j), __shfl_sync(0xffffffffu, gr, j + 1));
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                uint64_t acc[3] = {ax[k], ay[k], az[k]};
+                pair_interaction<false>(sj, gj, xi[k], yi[k], zi[k], soft2p, acc);
+                ax[k] = acc[0]; ay[k] = acc[1]; az[k] = acc[2];
+            }
+        }
+    }
+}
+
 // Scalar FFMA/FMUL/FADD version of the same block (13 issue slots per interaction).
 template <int R, int U>
 __device__ __forceinline__ void block_scalar(const float *__restrict__ sb, const float (&xi)[R], const float (&yi)[R],
@@ -290,7 +318,8 @@ __device__ __forceinline__ void block_scalar(const float *__restrict__ sb, const
 // R            targets per thread (register blocking)
 // TJB          AoSoA blocks (of 128 sources) per pipeline stage
 // ST           pipeline stages
-// MATH         0 = scalar FP32, 1 = packed f32x2, 2 = packed f32x2 with scalar-FFMA accumulation
+// MATH         0 = scalar FP32, 1 = packed f32x2, 2 = packed f32x2 with scalar-FFMA accumulation,
+//              3 = packed f32x2 with shuffle-broadcast sources (comparator)
 // WARP_PRIVATE each warp owns its stages and barriers (no CTA-wide barrier in the loop)
 // U            unroll of the 4-source inner step
 // MINB         min resident CTAs per SM for __launch_bounds__
@@ -375,7 +404,10 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
             uint64_t ax[R], ay[R], az[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) ax[k] = ay[k] = az[k] = 0ull;
-            for (uint32_t b = 0; b < nb; ++b) block_packed<R, U, MATH == 2>(sb + b * BLK_FLOATS, xi, yi, zi, soft2p, ax, ay, az);
+            for (uint32_t b = 0; b < nb; ++b) {
+                if (MATH == 3) block_packed_shfl<R>(sb + b * BLK_FLOATS, xi, yi, zi, soft2p, ax, ay, az);
+                else block_packed<R, U, MATH == 2>(sb + b * BLK_FLOATS, xi, yi, zi, soft2p, ax, ay, az);
+            }
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 float lo, hi;

@@ -176,7 +176,7 @@ template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MIN
 {
     Variant v;
     char nm[128];
-    snprintf(nm, sizeof nm, "%s_t%d_r%d_tj%d_st%d_%s_u%d_mb%d", MATH == 0 ? "sc" : (MATH == 1 ? "pk" : "ps"), THREADS, R, TJB, ST,
+    snprintf(nm, sizeof nm, "%s_t%d_r%d_tj%d_st%d_%s_u%d_mb%d", MATH == 0 ? "sc" : (MATH == 1 ? "pk" : (MATH == 2 ? "ps" : "px")), THREADS, R, TJB, ST,
              WP ? "warp" : "cta", U, MINB);
     v.name = nm;
     if (pad_smem) v.name += "_pad" + std::to_string(pad_smem / 1024) + "k";
@@ -193,7 +193,7 @@ template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MIN
 
 static void register_all()
 {
-    //            THR  R TJB ST MATH  WP    U MINB      MATH: 0 scalar, 1 packed, 2 packed + scalar accumulate
+    //            THR  R TJB ST MATH  WP    U MINB      MATH: 0 scalar, 1 packed, 2 packed + scalar accumulate, 3 packed + shuffle broadcast
     reg_variant<256, 2, 2, 3, 1, false, 2, 3>();
     reg_variant<256, 4, 2, 3, 1, false, 2, 2>();
     reg_variant<128, 8, 2, 3, 1, false, 1, 2>();
@@ -221,6 +221,8 @@ static void register_all()
     reg_variant<128, 4, 2, 3, 1, false, 2, 3>();
     reg_variant<128, 4, 2, 3, 1, false, 1, 4>();
     reg_variant<128, 8, 1, 3, 1, true, 1, 2>();
+    // sources broadcast by warp shuffles instead of same-address LDS.128
+    reg_variant<128, 8, 2, 3, 3, false, 1, 2>();
     // scalar FP32 comparator (13 issue slots / interaction)
     reg_variant<256, 4, 2, 3, 0, false, 1, 2>();
 }
