@@ -193,6 +193,10 @@ template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MIN
 
 static void register_all()
 {
+#ifdef KBENCH_ONLY_DEFAULT // schedule-knob experiments: -DKBENCH_ONLY_DEFAULT -DB200NB_KNOB_...=x builds in seconds
+    reg_variant<128, 8, 2, 3, 1, false, 1, 2>();
+    return;
+#endif
     //            THR  R TJB ST MATH  WP    U MINB      MATH: 0 scalar, 1 packed, 2 packed + scalar accumulate, 3 packed + shuffle broadcast
     reg_variant<256, 2, 2, 3, 1, false, 2, 3>();
     reg_variant<256, 4, 2, 3, 1, false, 2, 2>();
