@@ -131,6 +131,13 @@ int b200nb_n_local_gpus(const b200nb_ctx *ctx);
 uint64_t b200nb_allocated_bytes(const b200nb_ctx *ctx); /* device bytes, all local GPUs */
 uint64_t b200nb_launch_count(const b200nb_ctx *ctx);    /* kernels of this library launched so far */
 const char *b200nb_kernel_name(const b200nb_ctx *ctx);  /* force-kernel variant in use */
+/* How positions travel between GPUs each step (the role of the MPI_Allgatherv calls of
+ * SimulationNBodyMultiNode.cpp:93-148): "none" (one GPU); "nccl-allgather" (default) - in-place ncclAllGather on a
+ * communication stream, overlapped with the own-slice force launch; "p2p-push" - in-process multi-GPU with NVLink peer
+ * access, chosen with B200NB_EXCHANGE=p2p or when libnccl cannot be loaded: the integrator kernel stores the new
+ * positions of its slice into every GPU's double-buffered body array, one event per GPU is the only synchronisation.
+ * The two produce bit-identical results. */
+const char *b200nb_exchange_name(const b200nb_ctx *ctx);
 
 /* CUDA-event stopwatch on the library's own compute stream(s) (torch.cuda.Event cannot see them).
  * slot in [0,8); elapsed is the max over the local devices. */

@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
         "b200nb_allocated_bytes": (c_uint64, [ctx]),
         "b200nb_launch_count": (c_uint64, [ctx]),
         "b200nb_kernel_name": (c_char_p, [ctx]),
+        "b200nb_exchange_name": (c_char_p, [ctx]),
         "b200nb_event_record": (c_int, [ctx, c_int]),
         "b200nb_event_elapsed_ms": (c_int, [ctx, c_int, c_int, POINTER(c_float)]),
         "b200nb_profile_enable": (c_int, [ctx, c_int]),
@@ -282,6 +283,11 @@ class Context:
     @property
     def kernel_name(self) -> str:
         return self._L.b200nb_kernel_name(self._ctx).decode()
+
+    @property
+    def exchange_name(self) -> str:
+        """'none' | 'p2p-push' | 'nccl-allgather' (include/b200nb.h: b200nb_exchange_name)."""
+        return self._L.b200nb_exchange_name(self._ctx).decode()
 
     def event_record(self, slot: int):
         self._check(self._L.b200nb_event_record(self._ctx, slot), "b200nb_event_record")

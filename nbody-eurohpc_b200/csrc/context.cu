@@ -106,6 +106,8 @@ struct Shard {
     int rank = 0, device = 0;
     cudaStream_t s_compute = nullptr, s_comm = nullptr;
     cudaEvent_t ev_integrated = nullptr, ev_gathered = nullptr;
+    cudaEvent_t ev_pushed = nullptr; // p2p exchange: this shard's integrator has stored its new positions on every GPU
+    float *bodies_next = nullptr;    // p2p exchange: the other half of the double-buffered body array
     cudaEvent_t timer[N_TIMER_SLOTS] = {};
     float *bodies = nullptr, *vel = nullptr, *acc = nullptr, *mass = nullptr, *partial = nullptr, *stage = nullptr;
     double *energy_blocks = nullptr, *energy_out = nullptr;
@@ -141,6 +143,7 @@ struct b200nb_ctx {
     uint32_t k_per_slice = 1, rows = 1; // S = k_per_slice * n_ranks
     std::string kname;                  // variant name (+ "+sk" in stream-K mode)
     bool stream_k = false;              // stream-K decomposition instead of the (tile x chunk) grid
+    bool p2p = false;                   // exchange = peer stores from the integrator (in-process multi-GPU) instead of NCCL
     uint32_t sk_grid = 0;               // CTAs per stream-K launch (resident slots)
     uint32_t sk_rows_own = 0, sk_rows_rem = 0;
     std::vector<Shard> shards;
@@ -194,6 +197,7 @@ int alloc_shard(b200nb_ctx *c, Shard &s)
     CU(c, cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
     CU(c, cudaEventCreateWithFlags(&s.ev_integrated, cudaEventDisableTiming));
     CU(c, cudaEventCreateWithFlags(&s.ev_gathered, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&s.ev_pushed, cudaEventDisableTiming));
     for (auto &t : s.timer) CU(c, cudaEventCreate(&t));
     CU(c, cudaFuncSetAttribute(c->kv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kv->smem));
     CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s.occ, c->kv->fn, c->kv->threads, c->kv->smem));
@@ -213,6 +217,7 @@ int alloc_buffers(b200nb_ctx *c, Shard &s)
     const size_t L = c->L;
     auto dmalloc = [&](void **p, size_t bytes) -> cudaError_t { s.bytes += bytes; return cudaMalloc(p, bytes); };
     CU(c, dmalloc((void **)&s.bodies, c->total_pad * 16));
+    if (c->p2p) CU(c, dmalloc((void **)&s.bodies_next, c->total_pad * 16));
     CU(c, dmalloc((void **)&s.vel, 3 * L * 4));
     CU(c, dmalloc((void **)&s.acc, 3 * L * 4));
     CU(c, dmalloc((void **)&s.mass, L * 4));
@@ -292,6 +297,52 @@ int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
 int enqueue_gather(b200nb_ctx *c);
 int sync_all(b200nb_ctx *c);
 
+// In-process multi-GPU has two exchange steps.  Default: in-place ncclAllGather on a communication stream, which runs
+// entirely beside the own-slice force launch.  Alternative (B200NB_EXCHANGE=p2p, and automatically when libnccl cannot
+// be loaded): every GPU can address every other one (NVLink / NVSwitch peers), so the integrator stores the new
+// positions of its slice straight into the body array of every GPU (integrate_sm100.cuh: IntegrateArgs::out) and one
+// event per GPU is the only synchronisation; the body array is double-buffered so that a fast GPU never overwrites
+// positions a slower one is still reading.  Measured on 2 B200s the fused form is 0.1-1.4 % *slower*
+// (profiles/r01_exchange_p2p_vs_nccl.txt): the peer stores must be flushed before the integrator kernel can retire,
+// which puts an NVLink round trip on the compute stream's critical path, while the separate all-gather hides all of
+// its latency behind the own-slice launch.  Both paths produce bit-identical results (tested).
+int enable_p2p(b200nb_ctx *c)
+{
+    const char *e = getenv("B200NB_EXCHANGE");
+    if (e && !strcmp(e, "nccl")) return B200NB_OK;
+    if (e && *e && strcmp(e, "p2p"))
+        return fail(c, B200NB_EINVAL, "B200NB_EXCHANGE must be 'p2p' or 'nccl', not '%s'", e);
+    if (!(e && *e)) {
+        if (g_nccl.load()) return B200NB_OK; // default
+        e = nullptr;                         // no NCCL on this machine: try the peer path before giving up
+    }
+    if (c->shards.size() > (size_t)MAX_PUSH_TARGETS) {
+        if (e) return fail(c, B200NB_EINVAL, "B200NB_EXCHANGE=p2p supports at most %d GPUs", MAX_PUSH_TARGETS);
+        return B200NB_OK;
+    }
+    for (auto &a : c->shards)
+        for (auto &b : c->shards) {
+            if (a.device == b.device) continue;
+            int ok = 0;
+            CU(c, cudaDeviceCanAccessPeer(&ok, a.device, b.device));
+            if (!ok) {
+                if (e) return fail(c, B200NB_ECUDA, "B200NB_EXCHANGE=p2p: device %d cannot access device %d", a.device, b.device);
+                return B200NB_OK; // no peer path: NCCL
+            }
+        }
+    for (auto &a : c->shards) {
+        CU(c, cudaSetDevice(a.device));
+        for (auto &b : c->shards) {
+            if (a.device == b.device) continue;
+            const cudaError_t r = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (r == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); continue; }
+            CU(c, r);
+        }
+    }
+    c->p2p = true;
+    return B200NB_OK;
+}
+
 int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks, const std::vector<int> &ranks,
                   const std::vector<int> &devices, const void *nccl_id)
 {
@@ -350,10 +401,13 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
         c->sk_rows_rem = max_rows(c->nblk_total - nbs);
         c->rows = c->sk_rows_own + c->sk_rows_rem;
     }
+    if (n_ranks > 1 && ranks.size() == (size_t)n_ranks) {
+        if (int rc = enable_p2p(c)) return bail(rc);
+    }
     for (auto &s : c->shards)
         if (int rc = alloc_buffers(c, s)) return bail(rc);
 
-    if (n_ranks > 1) {
+    if (n_ranks > 1 && !c->p2p) {
         if (!g_nccl.load()) { c->err = g_nccl.err; return bail(B200NB_ENCCL); }
         ncclUniqueId id;
         if (nccl_id) memcpy(&id, nccl_id, sizeof id);
@@ -376,6 +430,18 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
         if (int rc = sync_all(c)) return bail(rc);
     }
     *out = c;
+    return B200NB_OK;
+}
+
+// the compute stream of `s` may not read remote slices before they have landed
+int wait_remote_positions(b200nb_ctx *c, Shard &s)
+{
+    if (!c->p2p) {
+        CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0));
+        return B200NB_OK;
+    }
+    for (auto &o : c->shards)
+        if (&o != &s) CU(c, cudaStreamWaitEvent(s.s_compute, o.ev_pushed, 0));
     return B200NB_OK;
 }
 
@@ -409,7 +475,7 @@ int enqueue_force_sk(b200nb_ctx *c)
         };
         CU(c, launch(0, nbs, 0)); // own slice: resident, overlaps the all-gather
         if (c->n_ranks > 1) {
-            CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0)); // remote slices must have landed
+            if (int rc = wait_remote_positions(c, s)) return rc;
             CU(c, launch(nbs, c->nblk_total - nbs, c->sk_rows_own));
         }
     }
@@ -449,8 +515,8 @@ int enqueue_force(b200nb_ctx *c)
         if (c->n_ranks == 1) {
             CU(c, launch(0, c->rows));
         } else {
-            CU(c, launch(0, c->k_per_slice));                          // own slice: resident, overlaps the all-gather
-            CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0)); // remote slices must have landed
+            CU(c, launch(0, c->k_per_slice)); // own slice: resident, overlaps the exchange
+            if (int rc = wait_remote_positions(c, s)) return rc;
             CU(c, launch(c->k_per_slice, c->rows - c->k_per_slice));
         }
     }
@@ -459,11 +525,24 @@ int enqueue_force(b200nb_ctx *c)
 
 int enqueue_integrate(b200nb_ctx *c, int mode, float dt)
 {
+    const bool moves = mode == IM_MURB || mode == IM_MURB_STORED || mode == IM_LF_KICK_DRIFT;
+    const bool push = c->p2p && moves;
     for (auto &s : c->shards) {
-        if (s.n_local == 0) continue;
         CU(c, cudaSetDevice(s.device));
+        if (push) {
+            // the buffers about to be overwritten were last read one position update ago: every GPU's kernels of
+            // that time precede its previous push in stream order, so waiting for those pushes is enough
+            if (int rc = wait_remote_positions(c, s)) return rc;
+        }
+        if (s.n_local == 0) continue;
         IntegrateArgs a{};
         a.bodies = s.bodies; a.vel = s.vel; a.acc = s.acc; a.partial = s.partial;
+        if (push) {
+            a.n_out = 0;
+            for (auto &o : c->shards) a.out[a.n_out++] = o.bodies_next;
+        } else {
+            a.out[0] = s.bodies; a.n_out = 1;
+        }
         a.rows = c->rows; a.L = (uint32_t)c->L; a.n_local = s.n_local;
         a.first = (uint64_t)s.rank * c->L; a.dt = dt; a.mode = mode;
         if (c->stream_k) {
@@ -477,13 +556,20 @@ int enqueue_integrate(b200nb_ctx *c, int mode, float dt)
         c->launches++;
         CU(c, cudaGetLastError());
     }
+    if (push) {
+        for (auto &s : c->shards) {
+            CU(c, cudaSetDevice(s.device));
+            CU(c, cudaEventRecord(s.ev_pushed, s.s_compute));
+            std::swap(s.bodies, s.bodies_next);
+        }
+    }
     return B200NB_OK;
 }
 
 // positions of the own slice changed: publish them to every other rank (in place, on the comm stream)
 int enqueue_gather(b200nb_ctx *c)
 {
-    if (c->n_ranks == 1) return B200NB_OK;
+    if (c->n_ranks == 1 || c->p2p) return B200NB_OK; // p2p: the integrator already stored the positions everywhere
     for (auto &s : c->shards) {
         CU(c, cudaSetDevice(s.device));
         CU(c, cudaEventRecord(s.ev_integrated, s.s_compute));
@@ -614,11 +700,12 @@ void b200nb_destroy(b200nb_ctx *c)
         if (s.s_comm) cudaStreamSynchronize(s.s_comm);
         if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
         for (auto e : s.prof) cudaEventDestroy(e);
-        cudaFree(s.bodies); cudaFree(s.vel); cudaFree(s.acc); cudaFree(s.mass); cudaFree(s.partial); cudaFree(s.stage);
+        cudaFree(s.bodies); cudaFree(s.bodies_next); cudaFree(s.vel); cudaFree(s.acc); cudaFree(s.mass); cudaFree(s.partial); cudaFree(s.stage);
         cudaFree(s.energy_blocks); cudaFree(s.energy_out); cudaFree(s.l2_scratch);
         for (auto t : s.timer) if (t) cudaEventDestroy(t);
         if (s.ev_integrated) cudaEventDestroy(s.ev_integrated);
         if (s.ev_gathered) cudaEventDestroy(s.ev_gathered);
+        if (s.ev_pushed) cudaEventDestroy(s.ev_pushed);
         if (s.s_compute) cudaStreamDestroy(s.s_compute);
         if (s.s_comm) cudaStreamDestroy(s.s_comm);
     }
@@ -634,6 +721,9 @@ int b200nb_upload(b200nb_ctx *c, const float *qx, const float *qy, const float *
     if (!qx || !qy || !qz || !m || !vx || !vy || !vz) return fail(c, B200NB_EINVAL, "upload: NULL array");
     DeviceGuard guard;
     const float *src[7] = {qx, qy, qz, m, vx, vy, vz};
+    if (c->p2p) { // peers may still be storing positions into this GPU's buffers
+        if (int rc = sync_all(c)) return rc;
+    }
     for (auto &s : c->shards) {
         CU(c, cudaSetDevice(s.device));
         // the previous step's gather may still be writing remote slices of `bodies`
@@ -645,6 +735,8 @@ int b200nb_upload(b200nb_ctx *c, const float *qx, const float *qy, const float *
                                                   s.mass, c->L, (uint64_t)s.rank * c->L);
         c->launches++;
         CU(c, cudaGetLastError());
+        if (c->p2p) // both halves of the double buffer carry G*m and the padding bodies; positions alternate
+            CU(c, cudaMemcpyAsync(s.bodies_next, s.bodies, c->total_pad * 16, cudaMemcpyDeviceToDevice, s.s_compute));
     }
     // host pointers are only borrowed for the call: the copies must have left them (pinned memory is truly async)
     for (auto &s : c->shards) {
@@ -882,6 +974,11 @@ uint64_t b200nb_allocated_bytes(const b200nb_ctx *c)
 }
 uint64_t b200nb_launch_count(const b200nb_ctx *c) { return c ? c->launches : 0; }
 const char *b200nb_kernel_name(const b200nb_ctx *c) { return c ? c->kname.c_str() : ""; }
+const char *b200nb_exchange_name(const b200nb_ctx *c)
+{
+    if (!c) return "";
+    return c->n_ranks == 1 ? "none" : (c->p2p ? "p2p-push" : "nccl-allgather");
+}
 
 int b200nb_event_record(b200nb_ctx *c, int slot)
 {

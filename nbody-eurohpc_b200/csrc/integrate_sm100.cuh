@@ -27,8 +27,15 @@ struct SkRows {
     uint32_t G, nb, row0;
 };
 
+constexpr int MAX_PUSH_TARGETS = 16;
+
 struct IntegrateArgs {
-    float *bodies;        // blocked full array; the slice [first, first+L) is updated in place
+    const float *bodies;  // blocked full array the current positions are read from
+    // Where the new positions of the slice [first, first+L) go.  One entry == `bodies`: in-place update (single GPU,
+    // or NCCL all-gather afterwards).  Several entries: the *other* buffer of the double-buffered body array on this
+    // GPU and on every peer GPU (peer pointers, stores travel over NVLink) - the integrator is also the exchange step.
+    float *out[MAX_PUSH_TARGETS];
+    int n_out;
     float *vel;           // [3][L] local velocities
     float *acc;           // [3][L] local accelerations
     const float *partial; // [rows][3][L]
@@ -88,9 +95,10 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
         const float axdt = __fmul_rn(ax, a.dt), aydt = __fmul_rn(ay, a.dt), azdt = __fmul_rn(az, a.dt);
         const double dt = (double)a.dt;
         const double qx = (double)a.bodies[ix], qy = (double)a.bodies[iy], qz = (double)a.bodies[iz];
-        a.bodies[ix] = (float)__dadd_rn(qx, __dmul_rn(__dadd_rn((double)vx, __dmul_rn((double)axdt, 0.5)), dt));
-        a.bodies[iy] = (float)__dadd_rn(qy, __dmul_rn(__dadd_rn((double)vy, __dmul_rn((double)aydt, 0.5)), dt));
-        a.bodies[iz] = (float)__dadd_rn(qz, __dmul_rn(__dadd_rn((double)vz, __dmul_rn((double)azdt, 0.5)), dt));
+        const float nx = (float)__dadd_rn(qx, __dmul_rn(__dadd_rn((double)vx, __dmul_rn((double)axdt, 0.5)), dt));
+        const float ny = (float)__dadd_rn(qy, __dmul_rn(__dadd_rn((double)vy, __dmul_rn((double)aydt, 0.5)), dt));
+        const float nz = (float)__dadd_rn(qz, __dmul_rn(__dadd_rn((double)vz, __dmul_rn((double)azdt, 0.5)), dt));
+        for (int d = 0; d < a.n_out; ++d) { a.out[d][ix] = nx; a.out[d][iy] = ny; a.out[d][iz] = nz; }
         a.vel[i] = __fadd_rn(vx, axdt);
         a.vel[L + i] = __fadd_rn(vy, aydt);
         a.vel[2 * L + i] = __fadd_rn(vz, azdt);
@@ -105,9 +113,10 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
     a.vel[i] = vx; a.vel[L + i] = vy; a.vel[2 * L + i] = vz;
     if (a.mode == IM_LF_KICK_DRIFT) { // drift, fp64 like the MUrB position update
         const double dt = (double)a.dt;
-        a.bodies[ix] = (float)__fma_rn((double)vx, dt, (double)a.bodies[ix]);
-        a.bodies[iy] = (float)__fma_rn((double)vy, dt, (double)a.bodies[iy]);
-        a.bodies[iz] = (float)__fma_rn((double)vz, dt, (double)a.bodies[iz]);
+        const float nx = (float)__fma_rn((double)vx, dt, (double)a.bodies[ix]);
+        const float ny = (float)__fma_rn((double)vy, dt, (double)a.bodies[iy]);
+        const float nz = (float)__fma_rn((double)vz, dt, (double)a.bodies[iz]);
+        for (int d = 0; d < a.n_out; ++d) { a.out[d][ix] = nx; a.out[d][iy] = ny; a.out[d][iz] = nz; }
     }
 }
 

@@ -307,15 +307,20 @@ def test_metrics_match_oracle_and_leapfrog_conserves_angular_momentum(b200, orac
         assert abs(after["mass"] - ref["mass"]) <= 1e-12 * ref["mass"]
 
 
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("integrator", [0, 1])
-def test_two_gpus_match_one(b200, oracle, integrator):
+def test_two_gpus_match_one(b200, oracle, integrator, exchange, monkeypatch):
+    """In-process sharding over 2 GPUs, with both exchange steps: the integrator storing its slice into every GPU's
+    double-buffered body array over NVLink (default) and the in-place ncclAllGather (B200NB_EXCHANGE=nccl)."""
     if _n_devices() < 2:
         pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("B200NB_EXCHANGE", exchange)
     n = 20000
     d = oracle.init_bodies("galaxy", n)
     outs = []
     for g in (1, 2):
         with make_ctx(b200, d, n_gpus=g) as ctx:
+            assert ctx.exchange_name == ("none" if g == 1 else {"p2p": "p2p-push", "nccl": "nccl-allgather"}[exchange])
             ctx.step(DT, integrator, 5)
             outs.append((ctx.download_state(), ctx.download_accel(), ctx.energy(), ctx.metrics()))
     # different chunking => different (fixed) summation order: agreement to a few fp32 ulps of the system size
@@ -330,6 +335,37 @@ def test_two_gpus_match_one(b200, oracle, integrator):
         assert abs(outs[0][3][k] - outs[1][3][k]) <= 1e-5 * l0, k
     for k in ("density_x", "density_y", "density_z", "com_x", "com_y", "com_z"):
         assert abs(outs[0][3][k] - outs[1][3][k]) <= 1e-5 * scale, k
+
+
+def test_two_gpus_p2p_matches_nccl_bitwise(b200, oracle, monkeypatch):
+    """Same sharding, same kernels, same summation order: the two exchange paths must agree bit for bit, also across
+    re-uploads, force-only passes, caller-supplied accelerations and an odd number of position updates (the double
+    buffer flips once per update)."""
+    if _n_devices() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 30001
+    d = oracle.init_bodies("random", n)
+    monkeypatch.delenv("B200NB_EXCHANGE", raising=False)
+    with b200.Context(n, G_F32, SOFT, 2) as ctx:
+        assert ctx.exchange_name == "nccl-allgather"  # the default (measured faster: all of it hides behind the own-slice launch)
+    res = {}
+    for exchange in ("p2p", "nccl"):
+        monkeypatch.setenv("B200NB_EXCHANGE", exchange)
+        with make_ctx(b200, d, n_gpus=2) as ctx:
+            ctx.step(DT, 0, 3)
+            ctx.accel()
+            a = ctx.download_accel()
+            ctx.integrate_host_accel(a[0], a[1], a[2], DT)
+            ctx.step(DT, 1, 4)
+            mid = ctx.download_state()
+            ctx.upload(mid["qx"], mid["qy"], mid["qz"], d["m"], mid["vx"], mid["vy"], mid["vz"])
+            ctx.step(DT, 0, 2)
+            res[exchange] = (ctx.download_state(), ctx.download_accel(), ctx.energy())
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(res["p2p"][0][k], res["nccl"][0][k]), k
+    for a, b in zip(res["p2p"][1], res["nccl"][1]):
+        assert np.array_equal(a, b)
+    assert res["p2p"][2] == res["nccl"][2]
 
 
 def test_torchrun_ranks_match_single_gpu():
