@@ -402,3 +402,20 @@ def test_patched_murb_cli():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "gpu+b200" in r.stdout and "Gflop/s" in r.stdout
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_catch2_and_cli_on_two_gpus(exchange):
+    """The same Catch2 binary and CLI with MURB_B200_NGPUS=2: the glue shards the targets over two devices in one
+    process (what a MUrB user gets), with either exchange step; every comparison against SimulationNBodyNaive and the
+    fp64 sums must still hold."""
+    if _n_devices() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, MURB_B200_NGPUS="2", B200NB_EXCHANGE=exchange)
+    r = subprocess.run([_ref_bin("murb-test-b200"), "[b200]"], capture_output=True, text=True, timeout=1500, env=env)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    r = subprocess.run([_ref_bin("murb_b200"), "-n", "100000", "-i", "10", "--nv", "--im", "gpu+b200+leapfrog", "--gf"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Gflop/s" in r.stdout
