@@ -129,6 +129,25 @@ def test_accel_other_softenings(b200, oracle, soft):
     assert max_rel_err(oracle.accel_f64(d, soft=soft), acc) <= ACC_TOL
 
 
+@pytest.mark.parametrize("n", [3, 31, 33, 255, 257, 1024, 2047, 2049, 4095, 4097, 12345, 20481])
+def test_accel_sizes_around_tile_boundaries(b200, oracle, n):
+    """Ragged sizes around every granularity of the launch (32-lane warp, 128-body block, 256 / 1024-target tiles, the
+    2048-body slice alignment, the small-N / large-N variant switch), random scheme, a softening drawn per size."""
+    rng = np.random.default_rng(n)
+    soft = float(10.0 ** rng.uniform(5.0, 8.5))
+    d = oracle.init_bodies("random" if n % 2 else "galaxy", n)
+    with make_ctx(b200, d, soft=soft) as ctx:
+        ctx.accel()
+        acc = ctx.download_accel()
+        ctx.step(DT, 0, 1)
+        after = ctx.download_state()
+    assert max_rel_err(oracle.accel_f64(d, soft=soft), acc) <= ACC_TOL
+    # one MUrB step from those accelerations, bit-exact against the integrator restatement (Bodies.cpp:259-278)
+    oracle.integrate_murb(d, acc[0], acc[1], acc[2], DT)
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(after[k].view(np.uint32), d[k].view(np.uint32)), k
+
+
 def test_zero_mass_and_coincident_bodies(b200, oracle):
     n = 300
     d = oracle.init_bodies("random", n)
