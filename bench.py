@@ -385,7 +385,8 @@ def run_b200_arm(args, rank, world, local_rank):
         "note": "compute-bound kernel: neither 'hbm' nor 'tensor' applies (SURVEY §8d). achieved = 12 FP32-pipe slots per "
                 "interaction counted as FMA (2 flop) x interactions per launch / CUDA-event launch duration; peak = "
                 f"148 SMs x 128 lanes x 2 x {max_mhz:.0f} MHz ({peak_src}; MEASURED_PEAKS.json has no FP32 entry), so "
-                "frac == 12*int/s / (148*128*f).",
+                "frac == 12*int/s / (148*128*f). The pipe peak is reachable: a pure FFMA2 loop measures 1.987 of 2.0 "
+                "warp-instr/clk/SM and FFMA 3.9 of 4.0 on this part (profiles/r01_microbench_pipes.txt).",
         "kernel": ctx.kernel_name, "avg_launch_ms": avg_launch_ms, "launches": force_launches,
         "kernel_share_of_step": force_ms / dev_ms,
         "kernel_gint_per_s_per_gpu": kernel_int_per_s / 1e9,
