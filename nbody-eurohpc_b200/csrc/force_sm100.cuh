@@ -131,6 +131,8 @@ struct ForceArgs {
     uint32_t chunk_first;        // first LOGICAL chunk of this launch; gridDim.y chunks are processed
     uint32_t chunk_rot;          // logical -> physical chunk rotation, (logical + rot) % S.  rot = k*rank makes
                                  // logical chunks [0,k) the rank's own slice (resident before the all-gather)
+    const uint32_t *chunk_tab;   // optional: {first block, end block} per LOGICAL chunk (rotation already applied);
+                                 // overrides the balanced split above, so chunks may have different lengths
     float soft2;
     unsigned long long *dbg;     // optional: per-CTA {clock64 start,end, globaltimer start,end}
 };
@@ -350,8 +352,14 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
     // balanced split of the source blocks over the S chunks; partial row = logical chunk index
     const uint32_t c = a.chunk_first + blockIdx.y;
     const uint32_t pc = (c + a.chunk_rot) % a.n_chunks_total;
-    const uint32_t b_begin = (uint32_t)(((uint64_t)a.src_nblk_total * pc) / a.n_chunks_total);
-    const uint32_t b_end = (uint32_t)(((uint64_t)a.src_nblk_total * (pc + 1)) / a.n_chunks_total);
+    uint32_t b_begin, b_end;
+    if (a.chunk_tab != nullptr) {
+        b_begin = __ldg(a.chunk_tab + 2 * c);
+        b_end = __ldg(a.chunk_tab + 2 * c + 1);
+    } else {
+        b_begin = (uint32_t)(((uint64_t)a.src_nblk_total * pc) / a.n_chunks_total);
+        b_end = (uint32_t)(((uint64_t)a.src_nblk_total * (pc + 1)) / a.n_chunks_total);
+    }
     const uint32_t nblk = b_end - b_begin;
     const uint32_t ntiles = (nblk + TJB - 1) / TJB;
     const float *chunk_src = a.src + (size_t)b_begin * BLK_FLOATS;

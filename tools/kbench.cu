@@ -288,6 +288,7 @@ int main(int argc, char **argv)
 {
     size_t n = 200000;
     int reps = 3, micro = 1, chunks_override = 0, check = 1;
+    std::string two_level;
     std::string filter, outpath = "gpurun_out/kbench.jsonl";
     for (int i = 1; i < argc; ++i) {
         auto arg = [&](const char *k) { return !strcmp(argv[i], k) && i + 1 < argc; };
@@ -298,6 +299,7 @@ int main(int argc, char **argv)
         else if (arg("--out")) outpath = argv[++i];
         else if (arg("--chunks")) chunks_override = atoi(argv[++i]);
         else if (arg("--check")) check = atoi(argv[++i]);
+        else if (arg("--two-level")) two_level = argv[++i]; // "Sbig,frac_small,ratio": decreasing chunk sizes, see below
     }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -366,6 +368,23 @@ int main(int argc, char **argv)
         a.tgt_blk0 = 0; a.tgt_stride = (uint32_t)p.n_pad;
         a.src_nblk_total = n_blocks; a.n_chunks_total = plan.n_chunks; a.chunk_first = 0; a.chunk_rot = 0;
         a.soft2 = p.soft2;
+        // experiment: Sbig equal chunks over (1 - frac) of the blocks, then small chunks (1/ratio of a big one) over
+        // the rest.  CTAs are dispatched in launch order, so the small ones fill the tail of the kernel.
+        uint32_t *d_tab = nullptr;
+        if (!two_level.empty()) {
+            int sb = 0; double frac = 0, ratio = 1;
+            if (sscanf(two_level.c_str(), "%d,%lf,%lf", &sb, &frac, &ratio) != 3 || sb < 1) { fprintf(stderr, "bad --two-level\n"); return 2; }
+            const uint32_t small_blocks = (uint32_t)(n_blocks * frac), big_blocks = n_blocks - small_blocks;
+            const uint32_t ss = std::max<uint32_t>(1, (uint32_t)std::lround(small_blocks / std::max(1.0, (double)big_blocks / sb / ratio)));
+            std::vector<uint32_t> tab;
+            for (int c = 0; c < sb; ++c) { tab.push_back((uint32_t)((uint64_t)big_blocks * c / sb)); tab.push_back((uint32_t)((uint64_t)big_blocks * (c + 1) / sb)); }
+            for (uint32_t c = 0; c < ss && small_blocks; ++c) { tab.push_back(big_blocks + (uint32_t)((uint64_t)small_blocks * c / ss)); tab.push_back(big_blocks + (uint32_t)((uint64_t)small_blocks * (c + 1) / ss)); }
+            plan.n_chunks = (uint32_t)(tab.size() / 2);
+            if (plan.n_chunks > p.partial_rows) { fprintf(stderr, "--two-level needs %u rows\n", plan.n_chunks); return 2; }
+            CK(cudaMalloc(&d_tab, tab.size() * 4));
+            CK(cudaMemcpy(d_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+            a.chunk_tab = d_tab; a.n_chunks_total = plan.n_chunks;
+        }
         dim3 grid(n_itiles, plan.n_chunks);
         const size_t ctas = (size_t)n_itiles * plan.n_chunks;
         a.dbg = ctas <= p.dbg_ctas ? p.d_dbg : nullptr;
