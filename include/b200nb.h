@@ -124,7 +124,8 @@ int b200nb_sync(b200nb_ctx *ctx);
 
 /* ---- introspection / measurement ------------------------------------------------------------------------------ */
 /* Targets per rank L (host only): rank r owns global bodies [r*L, min((r+1)*L, n)).  Contiguous, balanced to the
- * 2048-body launch granularity; the analogue of buildCountsDispls (SimulationNBodyMultiNode.cpp:76-91). */
+ * 256-body granularity (two 128-body AoSoA blocks; the launch rounds up to whole target tiles on its own); the
+ * analogue of buildCountsDispls (SimulationNBodyMultiNode.cpp:76-91). */
 uint64_t b200nb_slice_length(uint64_t n_bodies, int n_ranks);
 uint64_t b200nb_n_bodies(const b200nb_ctx *ctx);
 int b200nb_n_local_gpus(const b200nb_ctx *ctx);

@@ -98,7 +98,7 @@ const KernelVariant g_variants[] = {
     VARIANT("sc_t256_r4_tj2_st3_cta_u1_mb2", 256, 4, 2, 3, 0, false, 1, 2, 8.2),
 };
 constexpr int N_VARIANTS = sizeof(g_variants) / sizeof(g_variants[0]);
-constexpr uint64_t SLICE_ALIGN = 2048; // multiple of THREADS*R of every variant and of BLK
+constexpr uint64_t SLICE_ALIGN = 256;  // slice length granularity: a multiple of BLK; target tiles round up on their own (Lp)
 constexpr uint32_t MAX_ROWS = 256; // upper bound on partial rows (the 1 GiB cap in max_rows_for usually binds first for big N)
 constexpr int N_TIMER_SLOTS = 8;
 
@@ -137,6 +137,7 @@ struct b200nb_ctx {
     uint64_t n = 0;
     int n_ranks = 1;
     uint64_t L = 0, total_pad = 0, stage_stride = 0, total_pad_hint = 0;
+    uint64_t Lp = 0; // L rounded up to whole target tiles of the chosen variant: grid size and stride of the partial rows
     uint32_t nblk_total = 0;
     float G = 0.f, soft = 0.f, soft2 = 0.f;
     const KernelVariant *kv = nullptr;
@@ -221,7 +222,7 @@ int alloc_buffers(b200nb_ctx *c, Shard &s)
     CU(c, dmalloc((void **)&s.vel, 3 * L * 4));
     CU(c, dmalloc((void **)&s.acc, 3 * L * 4));
     CU(c, dmalloc((void **)&s.mass, L * 4));
-    CU(c, dmalloc((void **)&s.partial, (size_t)c->rows * 3 * L * 4));
+    CU(c, dmalloc((void **)&s.partial, (size_t)c->rows * 3 * c->Lp * 4));
     CU(c, dmalloc((void **)&s.stage, 7 * c->stage_stride * 4));
     const size_t eb = (L + ENERGY_THREADS - 1) / ENERGY_THREADS;
     CU(c, dmalloc((void **)&s.energy_blocks, eb * 8 * MR_COUNT));
@@ -262,8 +263,8 @@ uint32_t source_blocks(uint64_t n, uint64_t L, int n_ranks)
 ChunkPlan plan_for(const KernelVariant &kv, uint64_t n, uint64_t L, int n_sms, int occ, int n_ranks)
 {
     const uint32_t ti = kv.threads * kv.r;
-    return plan_chunks((uint32_t)(L / ti), source_blocks(n, L, n_ranks) / (uint32_t)n_ranks, (uint32_t)(n_sms * occ),
-                       (uint32_t)n_ranks, max_rows_for(L, n_ranks), (uint32_t)(2 * kv.tjb));
+    return plan_chunks((uint32_t)((L + ti - 1) / ti), source_blocks(n, L, n_ranks) / (uint32_t)n_ranks, (uint32_t)(n_sms * occ),
+                       (uint32_t)n_ranks, max_rows_for((L + ti - 1) / ti * ti, n_ranks), (uint32_t)(2 * kv.tjb));
 }
 
 // Between the large-tile default and the small-tile variant, take the one the planner expects to finish first:
@@ -291,7 +292,7 @@ int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
             if (occ_sk < 1) continue;
             const uint64_t G = (uint64_t)prop.multiProcessorCount * occ_sk;
             const uint64_t ti = (uint64_t)kv->threads * kv->r;
-            const uint64_t U = (c->L / ti) * (c->total_pad_hint / BLK);
+            const uint64_t U = ((c->L + ti - 1) / ti) * (c->total_pad_hint / BLK);
             t = (double)((U + G - 1) / G) * (double)ti * (double)occ_sk / kv->int_per_clk_sm;
         } else {
             const ChunkPlan p = plan_for(*kv, c->n, c->L, prop.multiProcessorCount, occ, c->n_ranks);
@@ -382,6 +383,10 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
         if (int rc = alloc_shard(c, c->shards[i])) return bail(rc);
     }
     const Shard &s0 = c->shards[0];
+    {
+        const uint64_t ti = (uint64_t)c->kv->threads * c->kv->r;
+        c->Lp = (c->L + ti - 1) / ti * ti;
+    }
     c->k_per_slice = plan_for(*c->kv, c->n, c->L, s0.n_sms, s0.occ, n_ranks).n_chunks;
     c->rows = c->k_per_slice * n_ranks;
     {
@@ -395,7 +400,7 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     c->kname = std::string(c->kv->name) + (c->stream_k ? "+sk" : "");
     if (c->stream_k) {
         const uint32_t ti = c->kv->threads * c->kv->r;
-        const uint32_t n_itiles = (uint32_t)(c->L / ti), nbs = (uint32_t)(c->L / BLK);
+        const uint32_t n_itiles = (uint32_t)(c->Lp / ti), nbs = (uint32_t)(c->L / BLK);
         const char *w = getenv("B200NB_SK_WAVES"); // experiment: CTAs = waves x resident slots
         c->sk_grid = (uint32_t)(s0.n_sms * s0.occ_sk) * (uint32_t)std::max(1, w ? atoi(w) : 1);
         auto max_rows = [&](uint32_t nb) {
@@ -464,10 +469,10 @@ int enqueue_force_sk(b200nb_ctx *c)
         ForceArgsSK a{};
         a.src = s.bodies; a.tgt = s.bodies; a.partial = s.partial;
         a.tgt_blk0 = (uint32_t)((uint64_t)s.rank * c->L / BLK);
-        a.tgt_stride = (uint32_t)c->L;
+        a.tgt_stride = (uint32_t)c->Lp; a.tgt_count = (uint32_t)c->L;
         a.src_nblk_total = c->nblk_total;
         a.blk_rot = nbs * (uint32_t)s.rank;
-        a.n_itiles = (uint32_t)(c->L / ti);
+        a.n_itiles = (uint32_t)(c->Lp / ti);
         a.soft2 = c->soft2;
         auto launch = [&](uint32_t lb0, uint32_t nb, uint32_t row0) -> cudaError_t {
             a.lb0 = lb0; a.nb = nb; a.row0 = row0;
@@ -501,13 +506,13 @@ int enqueue_force(b200nb_ctx *c)
         ForceArgs a{};
         a.src = s.bodies; a.tgt = s.bodies; a.partial = s.partial;
         a.tgt_blk0 = (uint32_t)((uint64_t)s.rank * c->L / BLK);
-        a.tgt_stride = (uint32_t)c->L;
+        a.tgt_stride = (uint32_t)c->Lp; a.tgt_count = (uint32_t)c->L;
         a.src_nblk_total = source_blocks(c->n, c->L, c->n_ranks);
         a.n_chunks_total = c->rows;
         a.chunk_rot = c->k_per_slice * (uint32_t)s.rank;
         a.soft2 = c->soft2;
         a.dbg = nullptr;
-        const uint32_t n_itiles = (uint32_t)(c->L / ti);
+        const uint32_t n_itiles = (uint32_t)(c->Lp / ti);
         auto launch = [&](uint32_t first, uint32_t count) -> cudaError_t {
             a.chunk_first = first;
             cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -551,10 +556,10 @@ int enqueue_integrate(b200nb_ctx *c, int mode, float dt)
         } else {
             a.out[0] = s.bodies; a.n_out = 1;
         }
-        a.rows = c->rows; a.L = (uint32_t)c->L; a.n_local = s.n_local;
+        a.rows = c->rows; a.L = (uint32_t)c->L; a.pstride = (uint32_t)c->Lp; a.n_local = s.n_local;
         a.first = (uint64_t)s.rank * c->L; a.dt = dt; a.mode = mode;
         if (c->stream_k) {
-            const uint32_t ti = c->kv->threads * c->kv->r, n_itiles = (uint32_t)(c->L / ti), nbs = (uint32_t)(c->L / BLK);
+            const uint32_t ti = c->kv->threads * c->kv->r, n_itiles = (uint32_t)(c->Lp / ti), nbs = (uint32_t)(c->L / BLK);
             a.sk_ti = ti;
             a.sk[0] = SkRows{(uint64_t)n_itiles * nbs, c->sk_grid, nbs, 0};
             const uint32_t nbr = c->nblk_total - nbs;

@@ -125,7 +125,9 @@ struct ForceArgs {
     const float *tgt;            // blocked bodies the targets are read from (same array on one GPU)
     float *partial;              // [rows][3][tgt_stride] partial accelerations
     uint32_t tgt_blk0;           // first target block inside `tgt`
-    uint32_t tgt_stride;         // floats per component row of `partial` (padded local target count)
+    uint32_t tgt_stride;         // floats per component row of `partial`: the local target count rounded up to whole tiles
+    uint32_t tgt_count;          // local targets (the slice length); the last tile may reach past it: those threads
+                                 // re-read the last target and their partial sums are never used
     uint32_t src_nblk_total;     // AoSoA blocks in the whole padded system (sources)
     uint32_t n_chunks_total;     // S: source chunks the system is cut into (a multiple of the rank count)
     uint32_t chunk_first;        // first LOGICAL chunk of this launch; gridDim.y chunks are processed
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
     float xi[R], yi[R], zi[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        const size_t il = (size_t)blockIdx.x * TI + (size_t)k * THREADS + threadIdx.x;
+        const size_t il = min((size_t)blockIdx.x * TI + (size_t)k * THREADS + threadIdx.x, (size_t)a.tgt_count - 1);
         const size_t ig = (size_t)a.tgt_blk0 * BLK + il;
         xi[k] = __ldg(a.tgt + blk_index(ig, 0));
         yi[k] = __ldg(a.tgt + blk_index(ig, 1));
@@ -471,7 +473,8 @@ struct ForceArgsSK {
     const float *tgt;          // blocked bodies the targets are read from
     float *partial;            // [rows][3][tgt_stride]
     uint32_t tgt_blk0;         // first target block inside `tgt`
-    uint32_t tgt_stride;       // floats per component row of `partial`
+    uint32_t tgt_stride;       // floats per component row of `partial` (whole tiles)
+    uint32_t tgt_count;        // local targets; threads of the last tile past it re-read the last target
     uint32_t src_nblk_total;   // NB: blocks of the whole padded system
     uint32_t blk_rot;          // logical -> physical block rotation (rank's first block): phys = (lb + rot) % NB
     uint32_t lb0, nb;          // logical block range [lb0, lb0 + nb) of this launch
@@ -529,7 +532,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel_sk(const ForceArgs
         float xi[R], yi[R], zi[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) {
-            const size_t il = (size_t)t * TI + (size_t)k * THREADS + threadIdx.x;
+            const size_t il = min((size_t)t * TI + (size_t)k * THREADS + threadIdx.x, (size_t)a.tgt_count - 1);
             const size_t ig = (size_t)a.tgt_blk0 * BLK + il;
             xi[k] = __ldg(a.tgt + blk_index(ig, 0));
             yi[k] = __ldg(a.tgt + blk_index(ig, 1));

@@ -38,9 +38,10 @@ struct IntegrateArgs {
     int n_out;
     float *vel;           // [3][L] local velocities
     float *acc;           // [3][L] local accelerations
-    const float *partial; // [rows][3][L]
+    const float *partial; // [rows][3][pstride]
     uint32_t rows;
-    uint32_t L;           // local slice length == row stride
+    uint32_t pstride;     // floats per component row of `partial` (slice length rounded up to whole target tiles)
+    uint32_t L;           // local slice length == stride of vel / acc
     uint32_t n_local;     // real (non-padding) bodies in the slice
     uint64_t first;       // global index of the first local body (multiple of BLK)
     float dt;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_local) return;
-    const size_t L = a.L;
+    const size_t L = a.L, P = a.pstride;
 
     float ax, ay, az;
     if (a.mode == IM_LF_KICK_DRIFT || a.mode == IM_MURB_STORED) {
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
         double sx = 0.0, sy = 0.0, sz = 0.0;
         if (a.sk_ti == 0) {
             for (uint32_t r = 0; r < a.rows; ++r) {
-                const float *p = a.partial + (size_t)r * 3 * L;
-                sx += (double)p[i]; sy += (double)p[L + i]; sz += (double)p[2 * L + i];
+                const float *p = a.partial + (size_t)r * 3 * P;
+                sx += (double)p[i]; sy += (double)p[P + i]; sz += (double)p[2 * P + i];
             }
         } else {
             const uint32_t t = i / a.sk_ti;
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
                 if (a.sk[l].units == 0) continue;
                 const uint32_t cnt = sk_rows_of_tile(t, a.sk[l].nb, a.sk[l].units, a.sk[l].G);
                 for (uint32_t r = 0; r < cnt; ++r) {
-                    const float *p = a.partial + (size_t)(a.sk[l].row0 + r) * 3 * L;
-                    sx += (double)p[i]; sy += (double)p[L + i]; sz += (double)p[2 * L + i];
+                    const float *p = a.partial + (size_t)(a.sk[l].row0 + r) * 3 * P;
+                    sx += (double)p[i]; sy += (double)p[P + i]; sz += (double)p[2 * P + i];
                 }
             }
         }

@@ -49,6 +49,7 @@ def test_bad_arguments(b200):
     L = b200.lib()
     assert L.b200nb_step(None, 1.0, 0, 1) == 1
     assert L.b200nb_init_bodies(7, 10, 0, *[None] * 8) == 1
-    assert L.b200nb_slice_length(200000, 1) == 200704
+    assert L.b200nb_slice_length(200000, 1) == 200192  # 256-body granularity
+    assert L.b200nb_slice_length(200000, 8) == 25088
     assert L.b200nb_slice_length(4194304, 8) == 524288
     assert L.b200nb_slice_length(5, 0) == 0

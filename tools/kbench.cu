@@ -365,7 +365,7 @@ int main(int argc, char **argv)
         if (chunks_override > 0) plan.n_chunks = std::min<uint32_t>((uint32_t)chunks_override, (uint32_t)p.partial_rows); // never past the allocated rows
         ForceArgs a{};
         a.src = p.d_bodies; a.tgt = p.d_bodies; a.partial = p.d_partial;
-        a.tgt_blk0 = 0; a.tgt_stride = (uint32_t)p.n_pad;
+        a.tgt_blk0 = 0; a.tgt_stride = (uint32_t)p.n_pad; a.tgt_count = (uint32_t)p.n_pad;
         a.src_nblk_total = n_blocks; a.n_chunks_total = plan.n_chunks; a.chunk_first = 0; a.chunk_rot = 0;
         a.soft2 = p.soft2;
         // experiment: Sbig equal chunks over (1 - frac) of the blocks, then small chunks (1/ratio of a big one) over
