@@ -157,7 +157,17 @@ def load_reference():
 
 def omp_env():
     # the reference's own recipe (README.md:78-89, SimulationNBodyOpenMP.cpp:99-109); must be set before libgomp starts
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every worker unless the user set it; the CPU arm runs on rank 0 alone (the
+    # other ranks exit), so it takes every core it is allowed to use.  B200NB_BENCH_OMP_THREADS pins it explicitly.
+    pinned = os.environ.get("B200NB_BENCH_OMP_THREADS")
+    if pinned:
+        os.environ["OMP_NUM_THREADS"] = pinned
+    elif "TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     os.environ.setdefault("OMP_DYNAMIC", "FALSE")
     os.environ.setdefault("OMP_PLACES", "cores")
