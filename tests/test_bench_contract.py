@@ -30,6 +30,21 @@ def test_reference_arm_line():
     assert "workload" in d["config"] and d["value"] > 0
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(REPO, "oracle", "_ref", "libmurbref.so")), reason="oracle/_ref not built")
+def test_reference_arm_takes_all_cores_under_torchrun(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm (rank 0 alone) must still use every allowed core."""
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    d = _run(["--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"], 600)
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["n_gpus"] == 2
+    monkeypatch.setenv("RANK", "1")  # the other ranks exit 0 without work and print nothing
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=REPO)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
 def test_reference_arm_falls_back_to_the_oracle_port(monkeypatch):
     """Without oracle/_ref (the reference could not be compiled) the arm times the oracle's C restatement instead."""
     monkeypatch.setenv("B200NB_BENCH_NO_REF", "1")
