@@ -54,6 +54,14 @@ typedef struct b200nb_ctx b200nb_ctx;
  * contiguously over the devices; for n_gpus > 1 positions are exchanged with ncclAllGather each step. */
 int b200nb_create(b200nb_ctx **out, uint64_t n_bodies, int n_gpus, float G, float soft);
 
+/* One process driving n_shards shards with an explicit placement: shard i (targets [i*L, (i+1)*L)) lives on CUDA device
+ * devices[i].  A device may be listed more than once ("virtual shards"): the slice arithmetic, chunk rotation, double
+ * buffering and exchange of the multi-GPU path then run on a single GPU, which is how the sharded path is tested on a
+ * one-GPU box.  Shards that share a device exchange positions with the p2p-push path (see b200nb_exchange_name; NCCL
+ * cannot hold the same GPU twice in a communicator).  n_shards <= 16.
+ * Replaces: the rank layout of SimulationNBodyMultiNode.cpp:62-91 (MPI ranks -> shards). */
+int b200nb_create_sharded(b200nb_ctx **out, uint64_t n_bodies, int n_shards, const int *devices, float G, float soft);
+
 /* One process per GPU (torchrun style): this process owns shard `rank` of `n_ranks` on CUDA device `device`.
  * nccl_id is the 128-byte ncclUniqueId made by b200nb_comm_unique_id() on rank 0 and broadcast by the caller
  * (ignored, may be NULL, when n_ranks == 1); like any ncclUniqueId it is good for ONE context — make a fresh one
@@ -70,13 +78,22 @@ const char *b200nb_last_error(const b200nb_ctx *ctx); /* ctx may be NULL: error 
  * Host SoA arrays of n_bodies floats, the layout of dataSoA_t (src/common/core/Bodies.hpp:15-24).
  * upload replaces CUDABodies::memcpyBuffersOnDevice (CUDABodies.cu:31-49) and devInitializeDevGM
  * (SimulationNBodyCUDATileFullDevice.cu:41-45): G*m is folded into the device layout once.  Every rank passes the
- * full arrays (the reference's MPI variant replicates state the same way, SimulationNBodyMultiNode.cpp:93-117). */
+ * full arrays (the reference's MPI variant replicates state the same way, SimulationNBodyMultiNode.cpp:93-117), but
+ * each shard copies only its own slice (and reads the last body, where the padding sits) across the host link; the
+ * position exchange of the step path then replicates the slices on every GPU.  Collective when n_ranks > 1. */
 int b200nb_upload(b200nb_ctx *ctx, const float *qx, const float *qy, const float *qz, const float *m, const float *vx,
                   const float *vy, const float *vz);
 
 /* Joins all devices, then copies positions and velocities of all n_bodies back (any pointer may be NULL).
  * Replaces the lazy D2H in CUDABodies::getDataSoA (CUDABodies.cu:63-93).  Collective when n_ranks > 1. */
 int b200nb_download_state(b200nb_ctx *ctx, float *qx, float *qy, float *qz, float *vx, float *vy, float *vz);
+
+/* The same for the local shards' own bodies only: entries [first, first + count) of each array are written (global
+ * indexing, see b200nb_slice_bounds), the rest is left untouched.  With one rank per process this is the D2H side of
+ * a sharded driver (every rank keeps the host copy of its own targets, the analogue of the send buffers of
+ * SimulationNBodyMultiNode.cpp:119-148) and moves 24 B per local body instead of 24 B per body per rank.  Not
+ * collective. */
+int b200nb_download_slice(b200nb_ctx *ctx, float *qx, float *qy, float *qz, float *vx, float *vy, float *vz);
 
 /* Accelerations of the last force pass (b200nb_accel or the last step).  Replaces getAccSoA()
  * (SimulationNBodyCUDAPropertyTracking.cu:308-319).  Collective when n_ranks > 1. */
@@ -127,6 +144,9 @@ int b200nb_sync(b200nb_ctx *ctx);
  * 256-body granularity (two 128-body AoSoA blocks; the launch rounds up to whole target tiles on its own); the
  * analogue of buildCountsDispls (SimulationNBodyMultiNode.cpp:76-91). */
 uint64_t b200nb_slice_length(uint64_t n_bodies, int n_ranks);
+/* Global body range [first, first + count) owned by the local_shard-th shard of this context (0 <= local_shard <
+ * b200nb_n_local_gpus); count is 0 for a shard that holds only padding. */
+int b200nb_slice_bounds(const b200nb_ctx *ctx, int local_shard, uint64_t *first, uint64_t *count);
 uint64_t b200nb_n_bodies(const b200nb_ctx *ctx);
 int b200nb_n_local_gpus(const b200nb_ctx *ctx);
 uint64_t b200nb_allocated_bytes(const b200nb_ctx *ctx); /* device bytes, all local GPUs */

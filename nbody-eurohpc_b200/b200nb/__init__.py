@@ -62,12 +62,15 @@ def lib() -> ctypes.CDLL:
     ctx = c_void_p
     sig = {
         "b200nb_create": (c_int, [POINTER(ctx), c_uint64, c_int, c_float, c_float]),
+        "b200nb_create_sharded": (c_int, [POINTER(ctx), c_uint64, c_int, POINTER(c_int), c_float, c_float]),
         "b200nb_create_rank": (c_int, [POINTER(ctx), c_uint64, c_float, c_float, c_int, c_int, c_int, c_void_p]),
         "b200nb_comm_unique_id": (c_int, [c_void_p]),
         "b200nb_destroy": (None, [ctx]),
         "b200nb_last_error": (c_char_p, [ctx]),
         "b200nb_upload": (c_int, [ctx] + [_FP] * 7),
         "b200nb_download_state": (c_int, [ctx] + [_FP] * 6),
+        "b200nb_download_slice": (c_int, [ctx] + [_FP] * 6),
+        "b200nb_slice_bounds": (c_int, [ctx, c_int, POINTER(c_uint64), POINTER(c_uint64)]),
         "b200nb_download_accel": (c_int, [ctx] + [_FP] * 3),
         "b200nb_step": (c_int, [ctx, c_float, c_int, c_int]),
         "b200nb_accel": (c_int, [ctx]),
@@ -172,11 +175,15 @@ class Context:
     """RAII wrapper of b200nb_ctx.  One process driving `n_gpus` devices, or one rank of a torchrun job."""
 
     def __init__(self, n: int, G: float = G_F32, soft: float = 2e8, n_gpus: int = 1, *, rank: int | None = None,
-                 n_ranks: int = 1, device: int = 0, nccl_id: bytes | None = None):
+                 n_ranks: int = 1, device: int = 0, nccl_id: bytes | None = None, devices: list[int] | None = None):
         self._L = lib()
         self._ctx = c_void_p()
         self.n = int(n)
-        if rank is None:
+        if devices is not None:  # explicit placement, one shard per entry; a device may repeat (virtual shards)
+            arr = (c_int * len(devices))(*devices)
+            rc = self._L.b200nb_create_sharded(byref(self._ctx), n, len(devices), arr, float(G), float(soft))
+            what = "b200nb_create_sharded"
+        elif rank is None:
             rc = self._L.b200nb_create(byref(self._ctx), n, n_gpus, float(G), float(soft))
             what = "b200nb_create"
         else:
@@ -225,15 +232,40 @@ class Context:
         self._check(self._L.b200nb_upload(self._ctx, *[_p(a) for a in arrs]), "b200nb_upload")
 
     def upload_raw(self, arrs):
-        """float32 C-contiguous arrays (e.g. pinned), no conversion, no checks beyond the C side."""
+        """float32 C-contiguous arrays (e.g. pinned) passed without conversion: the C side reads n floats from each."""
+        if len(arrs) != 7:
+            raise ValueError("expected 7 arrays: qx qy qz m vx vy vz")
+        for a in arrs:
+            if a.dtype != np.float32 or a.shape != (self.n,) or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"expected C-contiguous float32 arrays of {self.n} elements, got {a.dtype} {a.shape}")
         self._check(self._L.b200nb_upload(self._ctx, *[_p(a) for a in arrs]), "b200nb_upload")
 
-    def download_state(self, out: dict[str, np.ndarray] | None = None) -> dict[str, np.ndarray]:
+    _STATE = ("qx", "qy", "qz", "vx", "vy", "vz")
+
+    def _state_out(self, out):
         if out is None:
-            out = {k: np.empty(self.n, dtype=np.float32) for k in ("qx", "qy", "qz", "vx", "vy", "vz")}
-        self._check(self._L.b200nb_download_state(self._ctx, *[_p(out.get(k)) for k in ("qx", "qy", "qz", "vx", "vy", "vz")]),
-                    "b200nb_download_state")
+            return {k: np.empty(self.n, dtype=np.float32) for k in self._STATE}
+        for k in self._STATE:
+            a = out.get(k)
+            if a is not None and (a.dtype != np.float32 or a.shape != (self.n,) or not a.flags["C_CONTIGUOUS"]):
+                raise ValueError(f"{k}: expected a C-contiguous float32 array of {self.n} elements, got {a.dtype} {a.shape}")
         return out
+
+    def download_state(self, out: dict[str, np.ndarray] | None = None) -> dict[str, np.ndarray]:
+        out = self._state_out(out)
+        self._check(self._L.b200nb_download_state(self._ctx, *[_p(out.get(k)) for k in self._STATE]), "b200nb_download_state")
+        return out
+
+    def download_slice(self, out: dict[str, np.ndarray] | None = None) -> dict[str, np.ndarray]:
+        """Only the local shards' own bodies are written (global indexing); see slice_bounds()."""
+        out = self._state_out(out)
+        self._check(self._L.b200nb_download_slice(self._ctx, *[_p(out.get(k)) for k in self._STATE]), "b200nb_download_slice")
+        return out
+
+    def slice_bounds(self, local_shard: int = 0) -> tuple[int, int]:
+        first, count = c_uint64(), c_uint64()
+        self._check(self._L.b200nb_slice_bounds(self._ctx, local_shard, byref(first), byref(count)), "b200nb_slice_bounds")
+        return first.value, count.value
 
     def download_accel(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         a = [np.empty(self.n, dtype=np.float32) for _ in range(3)]
@@ -249,6 +281,9 @@ class Context:
 
     def integrate_host_accel(self, ax, ay, az, dt: float):
         a = [_f32(x) for x in (ax, ay, az)]
+        for x in a:
+            if x.shape != (self.n,):
+                raise ValueError(f"expected arrays of {self.n} floats, got {x.shape}")
         self._check(self._L.b200nb_integrate_host_accel(self._ctx, *[_p(x) for x in a], float(dt)), "b200nb_integrate_host_accel")
 
     def energy(self) -> float:

@@ -109,13 +109,19 @@ struct Shard {
     cudaEvent_t ev_pushed = nullptr; // p2p exchange: this shard's integrator has stored its new positions on every GPU
     float *bodies_next = nullptr;    // p2p exchange: the other half of the double-buffered body array
     cudaEvent_t timer[N_TIMER_SLOTS] = {};
-    float *bodies = nullptr, *vel = nullptr, *acc = nullptr, *mass = nullptr, *partial = nullptr, *stage = nullptr;
+    float *bodies = nullptr, *vel = nullptr, *acc = nullptr, *mass = nullptr, *partial = nullptr;
+    float *stage = nullptr;      // 7 host-layout SoA slices of L floats (H2D / D2H staging of the shard's own bodies)
+    float *stage_full = nullptr; // one rank per process only: 3 x stage_stride floats for a full-system position download (lazy)
     double *energy_blocks = nullptr, *energy_out = nullptr;
     void *l2_scratch = nullptr;
     ncclComm_t comm = nullptr;
     int n_sms = 0, occ = 0, occ_sk = 0;
     uint32_t n_local = 0; // real bodies in the slice
-    std::vector<cudaEvent_t> prof; // pairs (start, stop) around force launches
+    // profiling mode: event pairs (start, stop) around force launches.  In-flight pairs are folded into prof_ms and
+    // recycled once PROF_RING of them are pending, so a long profiled run neither grows nor creates events per launch.
+    std::vector<cudaEvent_t> prof, prof_free;
+    double prof_ms = 0.0;
+    uint64_t prof_n = 0;
     uint64_t bytes = 0;
 };
 
@@ -131,6 +137,7 @@ struct StepGraph {
 };
 constexpr int GRAPH_STEPS = 16;     // iterations per graph launch
 constexpr int GRAPH_MIN_STEPS = 32; // only worth capturing for longer runs
+constexpr size_t GRAPH_CACHE_MAX = 4; // executable graphs kept per context (oldest evicted)
 
 struct b200nb_ctx {
     std::vector<StepGraph> graphs;
@@ -223,7 +230,7 @@ int alloc_buffers(b200nb_ctx *c, Shard &s)
     CU(c, dmalloc((void **)&s.acc, 3 * L * 4));
     CU(c, dmalloc((void **)&s.mass, L * 4));
     CU(c, dmalloc((void **)&s.partial, (size_t)c->rows * 3 * c->Lp * 4));
-    CU(c, dmalloc((void **)&s.stage, 7 * c->stage_stride * 4));
+    CU(c, dmalloc((void **)&s.stage, 7 * L * 4));
     const size_t eb = (L + ENERGY_THREADS - 1) / ENERGY_THREADS;
     CU(c, dmalloc((void **)&s.energy_blocks, eb * 8 * MR_COUNT));
     CU(c, dmalloc((void **)&s.energy_out, 8 * MR_COUNT));
@@ -306,6 +313,44 @@ int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
 int enqueue_gather(b200nb_ctx *c);
 int sync_all(b200nb_ctx *c);
 
+constexpr size_t PROF_RING = 512; // pending (start, stop) pairs per shard before they are folded
+
+// fold every pending pair into the running total (joins the stop events) and recycle the events
+int prof_drain(b200nb_ctx *c, Shard &s)
+{
+    for (size_t i = 0; i + 1 < s.prof.size(); i += 2) {
+        float ms = 0.f;
+        CU(c, cudaEventSynchronize(s.prof[i + 1]));
+        CU(c, cudaEventElapsedTime(&ms, s.prof[i], s.prof[i + 1]));
+        s.prof_ms += ms;
+        s.prof_n++;
+    }
+    s.prof_free.insert(s.prof_free.end(), s.prof.begin(), s.prof.end());
+    s.prof.clear();
+    return B200NB_OK;
+}
+
+// start event of a profiled launch (recorded on the compute stream); the matching prof_stop records the other one
+int prof_start(b200nb_ctx *c, Shard &s)
+{
+    if (s.prof.size() >= 2 * PROF_RING)
+        if (int rc = prof_drain(c, s)) return rc;
+    cudaEvent_t e[2];
+    for (auto &ev : e) {
+        if (!s.prof_free.empty()) { ev = s.prof_free.back(); s.prof_free.pop_back(); }
+        else CU(c, cudaEventCreate(&ev));
+    }
+    s.prof.push_back(e[0]);
+    s.prof.push_back(e[1]);
+    CU(c, cudaEventRecord(e[0], s.s_compute));
+    return B200NB_OK;
+}
+int prof_stop(b200nb_ctx *c, Shard &s)
+{
+    CU(c, cudaEventRecord(s.prof.back(), s.s_compute));
+    return B200NB_OK;
+}
+
 // In-process multi-GPU has two exchange steps.  Default: in-place ncclAllGather on a communication stream, which runs
 // entirely beside the own-slice force launch.  Alternative (B200NB_EXCHANGE=p2p, and automatically when libnccl cannot
 // be loaded): every GPU can address every other one (NVLink / NVSwitch peers), so the integrator stores the new
@@ -318,6 +363,16 @@ int sync_all(b200nb_ctx *c);
 int enable_p2p(b200nb_ctx *c)
 {
     const char *e = getenv("B200NB_EXCHANGE");
+    // several shards on one device ("virtual shards", b200nb_create_sharded): NCCL refuses a communicator with the
+    // same GPU twice, and the peer path needs no peer at all there
+    bool shared_device = false;
+    for (size_t i = 0; i < c->shards.size(); ++i)
+        for (size_t j = i + 1; j < c->shards.size(); ++j) shared_device |= c->shards[i].device == c->shards[j].device;
+    if (shared_device) {
+        if (e && !strcmp(e, "nccl"))
+            return fail(c, B200NB_EINVAL, "B200NB_EXCHANGE=nccl cannot be used when several shards share one device");
+        e = "p2p";
+    }
     if (e && !strcmp(e, "nccl")) return B200NB_OK;
     if (e && *e && strcmp(e, "p2p"))
         return fail(c, B200NB_EINVAL, "B200NB_EXCHANGE must be 'p2p' or 'nccl', not '%s'", e);
@@ -474,22 +529,19 @@ int enqueue_force_sk(b200nb_ctx *c)
         a.blk_rot = nbs * (uint32_t)s.rank;
         a.n_itiles = (uint32_t)(c->Lp / ti);
         a.soft2 = c->soft2;
-        auto launch = [&](uint32_t lb0, uint32_t nb, uint32_t row0) -> cudaError_t {
+        auto launch = [&](uint32_t lb0, uint32_t nb, uint32_t row0) -> int {
             a.lb0 = lb0; a.nb = nb; a.row0 = row0;
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (c->profiling) {
-                cudaEventCreate(&e0); cudaEventCreate(&e1);
-                cudaEventRecord(e0, s.s_compute);
-            }
+            if (c->profiling) if (int rc = prof_start(c, s)) return rc;
             kv.fn_sk<<<c->sk_grid, kv.threads, kv.smem_sk, s.s_compute>>>(a);
-            if (c->profiling) { cudaEventRecord(e1, s.s_compute); s.prof.push_back(e0); s.prof.push_back(e1); }
+            if (c->profiling) if (int rc = prof_stop(c, s)) return rc;
             c->launches++;
-            return cudaGetLastError();
+            CU(c, cudaGetLastError());
+            return B200NB_OK;
         };
-        CU(c, launch(0, nbs, 0)); // own slice: resident, overlaps the all-gather
+        if (int rc = launch(0, nbs, 0)) return rc; // own slice: resident, overlaps the all-gather
         if (c->n_ranks > 1) {
             if (int rc = wait_remote_positions(c, s)) return rc;
-            CU(c, launch(nbs, c->nblk_total - nbs, c->sk_rows_own));
+            if (int rc = launch(nbs, c->nblk_total - nbs, c->sk_rows_own)) return rc;
         }
     }
     return B200NB_OK;
@@ -513,24 +565,21 @@ int enqueue_force(b200nb_ctx *c)
         a.soft2 = c->soft2;
         a.dbg = nullptr;
         const uint32_t n_itiles = (uint32_t)(c->Lp / ti);
-        auto launch = [&](uint32_t first, uint32_t count) -> cudaError_t {
+        auto launch = [&](uint32_t first, uint32_t count) -> int {
             a.chunk_first = first;
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (c->profiling) {
-                cudaEventCreate(&e0); cudaEventCreate(&e1);
-                cudaEventRecord(e0, s.s_compute);
-            }
+            if (c->profiling) if (int rc = prof_start(c, s)) return rc;
             kv.fn<<<dim3(n_itiles, count), kv.threads, kv.smem, s.s_compute>>>(a);
-            if (c->profiling) { cudaEventRecord(e1, s.s_compute); s.prof.push_back(e0); s.prof.push_back(e1); }
+            if (c->profiling) if (int rc = prof_stop(c, s)) return rc;
             c->launches++;
-            return cudaGetLastError();
+            CU(c, cudaGetLastError());
+            return B200NB_OK;
         };
         if (c->n_ranks == 1) {
-            CU(c, launch(0, c->rows));
+            if (int rc = launch(0, c->rows)) return rc;
         } else {
-            CU(c, launch(0, c->k_per_slice)); // own slice: resident, overlaps the exchange
+            if (int rc = launch(0, c->k_per_slice)) return rc; // own slice: resident, overlaps the exchange
             if (int rc = wait_remote_positions(c, s)) return rc;
-            CU(c, launch(c->k_per_slice, c->rows - c->k_per_slice));
+            if (int rc = launch(c->k_per_slice, c->rows - c->k_per_slice)) return rc;
         }
     }
     return B200NB_OK;
@@ -677,6 +726,22 @@ int b200nb_create(b200nb_ctx **out, uint64_t n_bodies, int n_gpus, float G, floa
     return create_common(out, n_bodies, G, soft, n_gpus, ranks, devices, nullptr);
 }
 
+int b200nb_create_sharded(b200nb_ctx **out, uint64_t n_bodies, int n_shards, const int *devices, float G, float soft)
+{
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible < 1)
+        return fail(nullptr, B200NB_ECUDA, "no CUDA device visible (libb200nb has no CPU fallback)");
+    if (n_shards < 1 || n_shards > MAX_PUSH_TARGETS || !devices)
+        return fail(nullptr, B200NB_EINVAL, "n_shards must be in [1, %d] with a device list", MAX_PUSH_TARGETS);
+    std::vector<int> ranks, devs;
+    for (int i = 0; i < n_shards; ++i) {
+        if (devices[i] < 0 || devices[i] >= visible) return fail(nullptr, B200NB_EINVAL, "device %d not visible", devices[i]);
+        ranks.push_back(i);
+        devs.push_back(devices[i]);
+    }
+    return create_common(out, n_bodies, G, soft, n_shards, ranks, devs, nullptr);
+}
+
 int b200nb_create_rank(b200nb_ctx **out, uint64_t n_bodies, float G, float soft, int rank, int n_ranks, int device,
                        const void *nccl_id)
 {
@@ -705,15 +770,19 @@ void b200nb_destroy(b200nb_ctx *c)
 {
     if (!c) return;
     DeviceGuard guard;
+    for (auto &s : c->shards) { // join before anything the streams may still be using goes away
+        if (cudaSetDevice(s.device) != cudaSuccess) continue;
+        if (s.s_compute) cudaStreamSynchronize(s.s_compute);
+        if (s.s_comm) cudaStreamSynchronize(s.s_comm);
+    }
     for (auto &g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto &s : c->shards) {
         if (cudaSetDevice(s.device) != cudaSuccess) continue;
-        if (s.s_compute) cudaStreamSynchronize(s.s_compute);
-        if (s.s_comm) cudaStreamSynchronize(s.s_comm);
         if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
         for (auto e : s.prof) cudaEventDestroy(e);
-        cudaFree(s.bodies); cudaFree(s.bodies_next); cudaFree(s.vel); cudaFree(s.acc); cudaFree(s.mass); cudaFree(s.partial); cudaFree(s.stage);
+        for (auto e : s.prof_free) cudaEventDestroy(e);
+        cudaFree(s.bodies); cudaFree(s.bodies_next); cudaFree(s.vel); cudaFree(s.acc); cudaFree(s.mass); cudaFree(s.partial); cudaFree(s.stage); cudaFree(s.stage_full);
         cudaFree(s.energy_blocks); cudaFree(s.energy_out); cudaFree(s.l2_scratch);
         for (auto t : s.timer) if (t) cudaEventDestroy(t);
         if (s.ev_integrated) cudaEventDestroy(s.ev_integrated);
@@ -727,6 +796,27 @@ void b200nb_destroy(b200nb_ctx *c)
 
 const char *b200nb_last_error(const b200nb_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
+// After an upload every shard holds only its own slice of the blocked array: replicate it everywhere (the same exchange
+// a step performs).  p2p: each shard copies its slice into both halves of every shard's double buffer (G*m and the
+// padding bodies live in the buffers too); NCCL: the in-place all-gather.
+static int publish_slices(b200nb_ctx *c)
+{
+    if (c->n_ranks == 1) return B200NB_OK;
+    if (!c->p2p) return enqueue_gather(c);
+    const size_t slice_floats = (size_t)c->L * 4;
+    for (auto &s : c->shards) {
+        CU(c, cudaSetDevice(s.device));
+        const float *mine = s.bodies + (size_t)s.rank * slice_floats;
+        for (auto &o : c->shards) {
+            if (&o != &s)
+                CU(c, cudaMemcpyAsync(o.bodies + (size_t)s.rank * slice_floats, mine, slice_floats * 4, cudaMemcpyDefault, s.s_compute));
+            CU(c, cudaMemcpyAsync(o.bodies_next + (size_t)s.rank * slice_floats, mine, slice_floats * 4, cudaMemcpyDefault, s.s_compute));
+        }
+        CU(c, cudaEventRecord(s.ev_pushed, s.s_compute));
+    }
+    return B200NB_OK;
+}
+
 int b200nb_upload(b200nb_ctx *c, const float *qx, const float *qy, const float *qz, const float *m, const float *vx,
                   const float *vy, const float *vz)
 {
@@ -737,20 +827,23 @@ int b200nb_upload(b200nb_ctx *c, const float *qx, const float *qy, const float *
     if (c->p2p) { // peers may still be storing positions into this GPU's buffers
         if (int rc = sync_all(c)) return rc;
     }
+    const float px = qx[c->n - 1], py = qy[c->n - 1], pz = qz[c->n - 1]; // where the padding bodies sit
     for (auto &s : c->shards) {
         CU(c, cudaSetDevice(s.device));
         // the previous step's gather may still be writing remote slices of `bodies`
         CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0));
-        for (int k = 0; k < 7; ++k)
-            CU(c, cudaMemcpyAsync(s.stage + (size_t)k * c->stage_stride, src[k], c->n * 4, cudaMemcpyHostToDevice, s.s_compute));
-        const int grid = (int)std::min<uint64_t>((c->total_pad + 255) / 256, (uint64_t)s.n_sms * 8);
-        pack_kernel<<<grid, 256, 0, s.s_compute>>>(s.stage, c->stage_stride, c->n, c->total_pad, c->G, s.bodies, s.vel,
-                                                  s.mass, c->L, (uint64_t)s.rank * c->L);
+        // only the shard's own bodies cross the host link (7 x 4 B each); the exchange below replicates the positions
+        const size_t first = (size_t)s.rank * c->L;
+        if (s.n_local > 0)
+            for (int k = 0; k < 7; ++k)
+                CU(c, cudaMemcpyAsync(s.stage + (size_t)k * c->L, src[k] + first, (size_t)s.n_local * 4, cudaMemcpyHostToDevice, s.s_compute));
+        const int grid = (int)std::min<uint64_t>((c->L + 255) / 256, (uint64_t)s.n_sms * 8);
+        pack_slice_kernel<<<grid, 256, 0, s.s_compute>>>(s.stage, (uint32_t)c->L, s.n_local, first, px, py, pz, c->G, s.bodies,
+                                                        s.vel, s.mass);
         c->launches++;
         CU(c, cudaGetLastError());
-        if (c->p2p) // both halves of the double buffer carry G*m and the padding bodies; positions alternate
-            CU(c, cudaMemcpyAsync(s.bodies_next, s.bodies, c->total_pad * 16, cudaMemcpyDeviceToDevice, s.s_compute));
     }
+    if (int rc = publish_slices(c)) return rc;
     // host pointers are only borrowed for the call: the copies must have left them (pinned memory is truly async)
     for (auto &s : c->shards) {
         CU(c, cudaSetDevice(s.device));
@@ -761,26 +854,75 @@ int b200nb_upload(b200nb_ctx *c, const float *qx, const float *qy, const float *
     return B200NB_OK;
 }
 
+// positions and velocities of the local shards' own bodies into the global-index host arrays (other entries untouched)
+static int download_local(b200nb_ctx *c, float *qx, float *qy, float *qz, float *vx, float *vy, float *vz)
+{
+    float *q[3] = {qx, qy, qz}, *v[3] = {vx, vy, vz};
+    for (auto &s : c->shards) {
+        if (s.n_local == 0) continue;
+        CU(c, cudaSetDevice(s.device));
+        const size_t first = (size_t)s.rank * c->L;
+        if (qx || qy || qz) {
+            const int grid = (int)std::min<uint64_t>((s.n_local + 255) / 256, (uint64_t)s.n_sms * 8);
+            unpack_positions_kernel<<<grid, 256, 0, s.s_compute>>>(s.bodies, first, s.n_local, s.stage, c->L);
+            c->launches++;
+            CU(c, cudaGetLastError());
+        }
+        for (int k = 0; k < 3; ++k) {
+            if (q[k])
+                CU(c, cudaMemcpyAsync(q[k] + first, s.stage + (size_t)k * c->L, (size_t)s.n_local * 4, cudaMemcpyDeviceToHost, s.s_compute));
+            if (v[k])
+                CU(c, cudaMemcpyAsync(v[k] + first, s.vel + (size_t)k * c->L, (size_t)s.n_local * 4, cudaMemcpyDeviceToHost, s.s_compute));
+        }
+    }
+    return sync_all(c);
+}
+
 int b200nb_download_state(b200nb_ctx *c, float *qx, float *qy, float *qz, float *vx, float *vy, float *vz)
 {
     if (!c) return B200NB_EINVAL;
     if (!c->uploaded) return fail(c, B200NB_ESTATE, "download_state before upload");
     DeviceGuard guard;
     if (int rc = sync_all(c)) return rc;
+    if (c->shards.size() == (size_t)c->n_ranks) // every shard is local: each one returns its own slice over its own link
+        return download_local(c, qx, qy, qz, vx, vy, vz);
+    // one rank per process: positions are replicated, so this rank's device has all of them after the gather
     if (qx || qy || qz) {
-        Shard &s = c->shards[0]; // positions are replicated: any shard has all of them after the gather
+        Shard &s = c->shards[0];
         CU(c, cudaSetDevice(s.device));
+        if (!s.stage_full) {
+            CU(c, cudaMalloc((void **)&s.stage_full, 3 * c->stage_stride * 4));
+            s.bytes += 3 * c->stage_stride * 4;
+        }
         const int grid = (int)std::min<uint64_t>((c->n + 255) / 256, (uint64_t)s.n_sms * 8);
-        unpack_positions_kernel<<<grid, 256, 0, s.s_compute>>>(s.bodies, c->n, s.stage, c->stage_stride);
+        unpack_positions_kernel<<<grid, 256, 0, s.s_compute>>>(s.bodies, 0, c->n, s.stage_full, c->stage_stride);
         c->launches++;
         CU(c, cudaGetLastError());
         float *dst[3] = {qx, qy, qz};
         for (int k = 0; k < 3; ++k)
             if (dst[k])
-                CU(c, cudaMemcpyAsync(dst[k], s.stage + (size_t)k * c->stage_stride, c->n * 4, cudaMemcpyDeviceToHost, s.s_compute));
+                CU(c, cudaMemcpyAsync(dst[k], s.stage_full + (size_t)k * c->stage_stride, c->n * 4, cudaMemcpyDeviceToHost, s.s_compute));
         CU(c, cudaStreamSynchronize(s.s_compute));
     }
     if (vx || vy || vz) return download_sliced(c, &Shard::vel, vx, vy, vz);
+    return B200NB_OK;
+}
+
+int b200nb_download_slice(b200nb_ctx *c, float *qx, float *qy, float *qz, float *vx, float *vy, float *vz)
+{
+    if (!c) return B200NB_EINVAL;
+    if (!c->uploaded) return fail(c, B200NB_ESTATE, "download_slice before upload");
+    DeviceGuard guard;
+    if (int rc = sync_all(c)) return rc;
+    return download_local(c, qx, qy, qz, vx, vy, vz);
+}
+
+int b200nb_slice_bounds(const b200nb_ctx *c, int local_shard, uint64_t *first, uint64_t *count)
+{
+    if (!c || local_shard < 0 || (size_t)local_shard >= c->shards.size()) return B200NB_EINVAL;
+    const Shard &s = c->shards[local_shard];
+    if (first) *first = std::min<uint64_t>((uint64_t)s.rank * c->L, c->n);
+    if (count) *count = s.n_local;
     return B200NB_OK;
 }
 
@@ -839,6 +981,13 @@ static int get_step_graph(b200nb_ctx *c, float dt, int integrator, StepGraph **o
     const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ei != cudaSuccess) return fail(c, B200NB_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+    // one executable graph per (integrator, dt): callers that change dt all the time would otherwise grow this
+    // list without bound.  Eviction is rare: join the stream first so no launch of the evicted graph is in flight.
+    while (c->graphs.size() >= GRAPH_CACHE_MAX) {
+        CU(c, cudaStreamSynchronize(s.s_compute));
+        cudaGraphExecDestroy(c->graphs.front().exec);
+        c->graphs.erase(c->graphs.begin());
+    }
     c->graphs.push_back(g);
     *out = &c->graphs.back();
     return B200NB_OK;
@@ -895,10 +1044,12 @@ int b200nb_integrate_host_accel(b200nb_ctx *c, const float *ax, const float *ay,
     for (auto &s : c->shards) {
         if (s.n_local == 0) continue;
         CU(c, cudaSetDevice(s.device));
+        // an in-place all-gather of a preceding asynchronous step may still be sending this slice from the comm stream
+        if (c->n_ranks > 1 && !c->p2p) CU(c, cudaStreamWaitEvent(s.s_compute, s.ev_gathered, 0));
         for (int k = 0; k < 3; ++k)
-            CU(c, cudaMemcpyAsync(s.stage + (size_t)k * c->stage_stride, src[k], c->n * 4, cudaMemcpyHostToDevice, s.s_compute));
-        load_acc_kernel<<<(s.n_local + 255) / 256, 256, 0, s.s_compute>>>(s.stage, c->stage_stride, (uint64_t)s.rank * c->L,
-                                                                       s.n_local, s.acc, c->L);
+            CU(c, cudaMemcpyAsync(s.stage + (size_t)k * c->L, src[k] + (size_t)s.rank * c->L, (size_t)s.n_local * 4,
+                                  cudaMemcpyHostToDevice, s.s_compute));
+        load_acc_kernel<<<(s.n_local + 255) / 256, 256, 0, s.s_compute>>>(s.stage, c->L, s.n_local, s.acc, c->L);
         c->launches++;
         CU(c, cudaGetLastError());
     }
@@ -1025,9 +1176,11 @@ int b200nb_profile_enable(b200nb_ctx *c, int on)
     if (!c) return B200NB_EINVAL;
     DeviceGuard guard;
     if (int rc = sync_all(c)) return rc;
-    for (auto &s : c->shards) {
-        for (auto e : s.prof) cudaEventDestroy(e);
+    for (auto &s : c->shards) { // pending pairs are dropped, their events kept for reuse
+        s.prof_free.insert(s.prof_free.end(), s.prof.begin(), s.prof.end());
         s.prof.clear();
+        s.prof_ms = 0.0;
+        s.prof_n = 0;
     }
     c->profiling = on != 0;
     return B200NB_OK;
@@ -1042,14 +1195,9 @@ int b200nb_profile_get(b200nb_ctx *c, double *force_ms_total, uint64_t *force_la
     uint64_t n = 0;
     for (auto &s : c->shards) {
         CU(c, cudaSetDevice(s.device));
-        double t = 0.0;
-        for (size_t i = 0; i + 1 < s.prof.size(); i += 2) {
-            float ms = 0.f;
-            CU(c, cudaEventElapsedTime(&ms, s.prof[i], s.prof[i + 1]));
-            t += ms;
-        }
-        mx = std::max(mx, t);
-        n = std::max<uint64_t>(n, s.prof.size() / 2);
+        if (int rc = prof_drain(c, s)) return rc;
+        mx = std::max(mx, s.prof_ms);
+        n = std::max<uint64_t>(n, s.prof_n);
     }
     if (force_ms_total) *force_ms_total = mx;
     if (force_launches) *force_launches = n;

@@ -103,12 +103,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
                  : "memory");
     return ok;
 }
-// Bounded wait: a pipeline bug traps (launch error) instead of hanging the GPU.
+// Bounded wait: a pipeline bug traps (sticky launch error, reported by the next b200nb call as B200NB_ECUDA) instead of
+// hanging the GPU.  The bound is wall time on %globaltimer, looked at every 4096 polls, not a poll count: a slow but
+// legitimate completion (compute-sanitizer, cuda-gdb, time-slicing, preemption) must not kill the context.
+#ifndef B200NB_MBAR_TIMEOUT_NS
+#define B200NB_MBAR_TIMEOUT_NS 20000000000ull // 20 s; define as 0 to wait forever
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if (B200NB_MBAR_TIMEOUT_NS != 0 && (++spins & 0xfffu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > B200NB_MBAR_TIMEOUT_NS) __trap();
+        }
     }
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).

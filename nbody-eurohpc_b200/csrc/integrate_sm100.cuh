@@ -122,52 +122,51 @@ __global__ void __launch_bounds__(256) integrate_kernel(const IntegrateArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------- pack / unpack
-// stage: 7 host-layout SoA arrays (qx qy qz m vx vy vz), each `stride` floats.  Builds the blocked array for ALL
-// total_pad bodies (padding: G*m = 0 at the position of the last real body, so it adds exactly 0 and cannot create
-// a singularity that a real pair does not have) and the local slice of velocities and masses.
-__global__ void __launch_bounds__(256) pack_kernel(const float *__restrict__ stage, size_t stride, size_t n,
-                                                  size_t total_pad, float G, float *__restrict__ bodies,
-                                                  float *__restrict__ vel, float *__restrict__ mass, size_t L,
-                                                  size_t first)
+// Host <-> device layout conversion for ONE shard's slice (global bodies [first, first + L)).
+// stage: 7 host-layout SoA slices (qx qy qz m vx vy vz), each L floats, the first n_local of each valid.  Writes the
+// slice's AoSoA blocks (positions + G*m) into `bodies` and the local velocities and masses.  Padding bodies (slice
+// entries past n_local) carry G*m = 0 at (px,py,pz) = the position of the last real body of the system, so they add
+// exactly 0 and cannot create a singularity that a real pair does not have.
+__global__ void __launch_bounds__(256) pack_slice_kernel(const float *__restrict__ stage, uint32_t L, uint32_t n_local,
+                                                        size_t first, float px, float py, float pz, float G,
+                                                        float *__restrict__ bodies, float *__restrict__ vel,
+                                                        float *__restrict__ mass)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pad; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t s = i < n ? i : n - 1;
-        const float m = i < n ? stage[3 * stride + i] : 0.f;
-        bodies[blk_index(i, 0)] = stage[s];
-        bodies[blk_index(i, 1)] = stage[stride + s];
-        bodies[blk_index(i, 2)] = stage[2 * stride + s];
+    for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < L; li += gridDim.x * blockDim.x) {
+        const bool real = li < n_local;
+        const size_t i = first + li;
+        const float m = real ? stage[3 * (size_t)L + li] : 0.f;
+        bodies[blk_index(i, 0)] = real ? stage[li] : px;
+        bodies[blk_index(i, 1)] = real ? stage[(size_t)L + li] : py;
+        bodies[blk_index(i, 2)] = real ? stage[2 * (size_t)L + li] : pz;
         bodies[blk_index(i, 3)] = __fmul_rn(G, m); // devInitializeDevGM: GM[i] = G * m[i]
-        if (i >= first && i < first + L) {
-            const size_t li = i - first;
-            const bool real = i < n;
-            vel[li] = real ? stage[4 * stride + i] : 0.f;
-            vel[L + li] = real ? stage[5 * stride + i] : 0.f;
-            vel[2 * L + li] = real ? stage[6 * stride + i] : 0.f;
-            mass[li] = m;
-        }
+        vel[li] = real ? stage[4 * (size_t)L + li] : 0.f;
+        vel[(size_t)L + li] = real ? stage[5 * (size_t)L + li] : 0.f;
+        vel[2 * (size_t)L + li] = real ? stage[6 * (size_t)L + li] : 0.f;
+        mass[li] = m;
     }
 }
 
-// blocked positions -> three SoA arrays of `stride` floats (all n bodies; positions are replicated on every GPU)
-__global__ void __launch_bounds__(256) unpack_positions_kernel(const float *__restrict__ bodies, size_t n,
+// blocked positions of bodies [first, first + count) -> three SoA arrays of `stride` floats (entry 0 = body `first`)
+__global__ void __launch_bounds__(256) unpack_positions_kernel(const float *__restrict__ bodies, size_t first, size_t count,
                                                               float *__restrict__ stage, size_t stride)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        stage[i] = bodies[blk_index(i, 0)];
-        stage[stride + i] = bodies[blk_index(i, 1)];
-        stage[2 * stride + i] = bodies[blk_index(i, 2)];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        stage[i] = bodies[blk_index(first + i, 0)];
+        stage[stride + i] = bodies[blk_index(first + i, 1)];
+        stage[2 * stride + i] = bodies[blk_index(first + i, 2)];
     }
 }
 
-// load caller-supplied accelerations (host SoA staged at `stage`, 3 x stride) into the local acc slice
-__global__ void __launch_bounds__(256) load_acc_kernel(const float *__restrict__ stage, size_t stride, size_t first,
-                                                      uint32_t n_local, float *__restrict__ acc, size_t L)
+// load caller-supplied accelerations of the slice (host SoA slices staged at `stage`, 3 x stride) into the local acc
+__global__ void __launch_bounds__(256) load_acc_kernel(const float *__restrict__ stage, size_t stride, uint32_t n_local,
+                                                      float *__restrict__ acc, size_t L)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_local) return;
-    acc[i] = stage[first + i];
-    acc[L + i] = stage[stride + first + i];
-    acc[2 * L + i] = stage[2 * stride + first + i];
+    acc[i] = stage[i];
+    acc[L + i] = stage[stride + i];
+    acc[2 * L + i] = stage[2 * stride + i];
 }
 
 // ---------------------------------------------------------------------------------------------- metrics

@@ -28,6 +28,8 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["value"] > 0
+    # the arm runs the configuration itself when it fits its CPU budget (2+1 iterations at n = 200 000 do)
+    assert d["config"]["bodies"] == 200000 and d["sample_bodies"] == 200000 and d["cpu_baseline"]["same_config"] is True
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(REPO, "oracle", "_ref", "libmurbref.so")), reason="oracle/_ref not built")
@@ -55,8 +57,9 @@ def test_reference_arm_falls_back_to_the_oracle_port(monkeypatch):
 
 @pytest.mark.gpu
 def test_b200_arm_line():
-    d = _run(["--steps", "5", "--warmup", "3", "--no-cpu", "--no-scaling-base"], 900)
-    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d)
+    d = _run(["--steps", "5", "--warmup", "3", "--no-cpu", "--no-scaling-base", "--no-side-legs"], 900)
+    assert BASE_KEYS | {"gpu_launches", "clocks", "roofline", "parity"} <= set(d)
+    assert d["parity"]["ok"] is True and d["parity"]["max_rel_err"] <= 1e-5 and d["parity"]["targets"] >= 40
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["dtype"] == "f32" and d["vs_baseline"] is None
     assert d["gpu_launches"] == 10                        # one force + one integrator launch per step
     assert d["e2e"]["h2d_bytes_per_step"] == 7 * 4 * 200000 and d["e2e"]["d2h_bytes_per_step"] == 6 * 4 * 200000

@@ -132,7 +132,7 @@ def test_accel_other_softenings(b200, oracle, soft):
 @pytest.mark.parametrize("n", [3, 31, 33, 255, 257, 1024, 2047, 2049, 4095, 4097, 12345, 20481])
 def test_accel_sizes_around_tile_boundaries(b200, oracle, n):
     """Ragged sizes around every granularity of the launch (32-lane warp, 128-body block, 256 / 1024-target tiles, the
-    2048-body slice alignment, the small-N / large-N variant switch), random scheme, a softening drawn per size."""
+    256-body slice alignment, the small-N / large-N variant switch), random scheme, a softening drawn per size."""
     rng = np.random.default_rng(n)
     soft = float(10.0 ** rng.uniform(5.0, 8.5))
     d = oracle.init_bodies("random" if n % 2 else "galaxy", n)
@@ -326,6 +326,118 @@ def test_metrics_match_oracle_and_leapfrog_conserves_angular_momentum(b200, orac
         assert abs(after["mass"] - ref["mass"]) <= 1e-12 * ref["mass"]
 
 
+def _boundary_targets(n, L, shards, extra=24, seed=3):
+    """Targets on both sides of every slice boundary (last body of shard k, first body of shard k+1), the ends of the
+    system and a few random ones."""
+    idx = [0, n - 1]
+    for k in range(1, shards):
+        idx += [k * L - 2, k * L - 1, k * L, k * L + 1]
+    idx += list(np.random.default_rng(seed).integers(0, n, extra))
+    return np.unique(np.clip(np.array(idx, dtype=np.int64), 0, n - 1)).astype(np.uint64)
+
+
+@pytest.mark.parametrize("shards", [2, 3, 4, 8])
+@pytest.mark.parametrize("integrator", [0, 1])
+def test_virtual_shards_match_one_shard(b200, oracle, shards, integrator):
+    """The sharded path (SimulationNBodyMultiNode.cpp:76-148 analogue) on ONE device: `shards` shards all placed on
+    device 0 (b200nb_create_sharded).  Slice arithmetic, the logical->physical chunk rotation, the own/remote launch
+    split, the double-buffered body array and the exchange step (integrator stores into every shard's buffer) all run;
+    only the NVLink hop is missing.  Checked against (1) a single-shard context, (2) the fp64 oracle on targets
+    straddling every slice boundary after two exchanges."""
+    n = 30001 if integrator else 20000
+    scheme = "random" if integrator else "galaxy"
+    d = oracle.init_bodies(scheme, n)
+    L = b200.slice_length(n, shards)
+    outs = []
+    for devs in ([0], [0] * shards):
+        with b200.Context(n, G_F32, SOFT, devices=devs) as ctx:
+            assert ctx.n_local_gpus == len(devs)
+            assert ctx.exchange_name == ("none" if len(devs) == 1 else "p2p-push")
+            ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+            ctx.step(DT, integrator, 5)
+            st, acc, e, m = ctx.download_state(), ctx.download_accel(), ctx.energy(), ctx.metrics()
+            ctx.accel()  # force pass on the positions the last exchange published
+            outs.append((st, acc, e, m, ctx.download_accel()))
+    one, many = outs
+    scale = max(float(np.abs(one[0][c]).max()) for c in ("qx", "qy", "qz"))
+    for c in ("qx", "qy", "qz"):
+        assert np.all(np.abs(one[0][c].astype(np.float64) - many[0][c]) <= 1e-6 * scale), c
+    for c in ("vx", "vy", "vz"):
+        assert np.all(np.abs(one[0][c].astype(np.float64) - many[0][c]) <= 1e-5 * float(np.abs(one[0][c]).max())), c
+    assert max_rel_err(one[1], many[1]) <= 2e-6
+    assert abs(one[2] - many[2]) <= 1e-6 * abs(one[2])
+    l0 = float(np.linalg.norm([one[3][k] for k in ("ang_x", "ang_y", "ang_z")]))
+    for k in ("ang_x", "ang_y", "ang_z"):
+        assert abs(one[3][k] - many[3][k]) <= 1e-5 * l0, k
+    # fp64 oracle on the sharded run's own positions, targets on both sides of every slice boundary
+    idx = _boundary_targets(n, L, shards)
+    moved = dict(d)
+    moved.update({k: many[0][k] for k in ("qx", "qy", "qz")})
+    ii = idx.astype(np.int64)
+    err = max_rel_err(oracle.accel_f64(moved, idx), [a[ii] for a in many[4]])
+    assert err <= ACC_TOL, err
+
+
+@pytest.mark.parametrize("n,shards", [(300, 4), (257, 2), (1, 2), (5000, 16), (100000, 8)])
+def test_virtual_shards_ragged(b200, oracle, n, shards):
+    """Ragged shardings: a partly filled last shard, shards with no body at all (n=300 over 4 shards of 256: 256 + 44 +
+    0 + 0), the 16-shard maximum, and N = 100k over 8 shards (12 544-body slices, small-tile variant)."""
+    d = oracle.init_bodies("random", n)
+    with b200.Context(n, G_F32, SOFT, devices=[0] * shards) as ctx:
+        ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+        rt = ctx.download_state()
+        for k in ("qx", "qy", "qz", "vx", "vy", "vz"):  # layout round trip through the sharded buffers: exact
+            assert np.array_equal(rt[k].view(np.uint32), d[k].view(np.uint32)), k
+        ctx.step(DT, 0, 3)
+        ctx.accel()
+        st, acc = ctx.download_state(), ctx.download_accel()
+        ctx.step(DT, 0, 1)
+        after = ctx.download_state()
+    if n == 1:
+        assert all(float(a[0]) == 0.0 for a in acc)
+        return
+    idx = _boundary_targets(n, b200.slice_length(n, shards), shards)
+    moved = dict(d)
+    moved.update(st)
+    ii = idx.astype(np.int64)
+    assert max_rel_err(oracle.accel_f64(moved, idx), [a[ii] for a in acc]) <= ACC_TOL
+    # one more MUrB step from those accelerations: the sharded integrator is bit-exact against the restatement
+    oracle.integrate_murb(moved, acc[0], acc[1], acc[2], DT)
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(after[k].view(np.uint32), moved[k].view(np.uint32)), k
+
+
+def test_virtual_shards_reupload_and_host_accel(b200, oracle):
+    """The double buffer flips once per position update: re-uploads, force-only passes, caller-supplied accelerations
+    and an odd number of updates must leave a sharded context in the same state as a single-shard one (bitwise for the
+    integrator-only part, which does not depend on the summation order)."""
+    n = 9000
+    d = oracle.init_bodies("galaxy", n)
+    i = np.arange(n, dtype=np.float32)
+    ax, ay, az = i + 1, np.full(n, 3.0, np.float32), np.float32(n) - i
+    res = []
+    for devs in ([0], [0, 0, 0]):
+        with b200.Context(n, G_F32, SOFT, devices=devs) as ctx:
+            ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+            for _ in range(3):
+                ctx.integrate_host_accel(ax, ay, az, 0.01)
+            mid = ctx.download_state()
+            ctx.upload(mid["qx"], mid["qy"], mid["qz"], d["m"], mid["vx"], mid["vy"], mid["vz"])
+            ctx.integrate_host_accel(ax, ay, az, 0.01)
+            res.append(ctx.download_state())
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(res[0][k].view(np.uint32), res[1][k].view(np.uint32)), k
+
+
+def test_virtual_shards_reject_nccl(b200, monkeypatch):
+    monkeypatch.setenv("B200NB_EXCHANGE", "nccl")
+    with pytest.raises(b200.B200Error) as e:
+        b200.Context(1000, G_F32, SOFT, devices=[0, 0])
+    assert e.value.code == 1  # EINVAL: NCCL cannot hold one GPU twice
+    with pytest.raises(b200.B200Error):
+        b200.Context(1000, G_F32, SOFT, devices=[0] * 17)
+
+
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("integrator", [0, 1])
 def test_two_gpus_match_one(b200, oracle, integrator, exchange, monkeypatch):
@@ -385,6 +497,23 @@ def test_two_gpus_p2p_matches_nccl_bitwise(b200, oracle, monkeypatch):
     for a, b in zip(res["p2p"][1], res["nccl"][1]):
         assert np.array_equal(a, b)
     assert res["p2p"][2] == res["nccl"][2]
+    # and two virtual shards on device 0 (what the one-GPU test box runs) are the same arithmetic as two real GPUs
+    monkeypatch.delenv("B200NB_EXCHANGE", raising=False)
+    with b200.Context(n, G_F32, SOFT, devices=[0, 0]) as ctx:
+        ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+        ctx.step(DT, 0, 3)
+        ctx.accel()
+        a = ctx.download_accel()
+        ctx.integrate_host_accel(a[0], a[1], a[2], DT)
+        ctx.step(DT, 1, 4)
+        mid = ctx.download_state()
+        ctx.upload(mid["qx"], mid["qy"], mid["qz"], d["m"], mid["vx"], mid["vy"], mid["vz"])
+        ctx.step(DT, 0, 2)
+        virt = (ctx.download_state(), ctx.download_accel(), ctx.energy())
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(virt[0][k], res["nccl"][0][k]), k
+    for a, b in zip(virt[1], res["nccl"][1]):
+        assert np.array_equal(a, b)
 
 
 def test_torchrun_ranks_match_single_gpu():
