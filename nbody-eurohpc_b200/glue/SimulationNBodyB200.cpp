@@ -1,5 +1,6 @@
 #include "SimulationNBodyB200.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -7,6 +8,7 @@
 #include <fstream>
 #include <iomanip>
 #include <limits>
+#include <stdexcept>
 
 #include "b200nb.h"
 
@@ -121,8 +123,28 @@ std::shared_ptr<Bodies<float>> B200BodiesAllocator::allocate_shared() const
 // ================================================================================================ simulation
 SimulationNBodyB200::SimulationNBodyB200(const BodiesAllocatorInterface<float> &allocator, const float soft,
                                          const bool leapfrog)
-    : SimulationNBodyInterface<float>(allocator, soft), integrator(leapfrog ? B200NB_INTEGRATOR_LEAPFROG : B200NB_INTEGRATOR_MURB)
+    : SimulationNBodyInterface<float>(allocator, soft),
+      HistoryTrackingInterface<double>(std::make_shared<SimulationHistory<double>>(0))
 {
+    this->init(leapfrog);
+}
+
+SimulationNBodyB200::SimulationNBodyB200(const BodiesAllocatorInterface<float> &allocator,
+                                         std::shared_ptr<SimulationHistory<double>> history, const float soft,
+                                         const bool leapfrog)
+    : SimulationNBodyInterface<float>(allocator, soft), HistoryTrackingInterface<double>(history)
+{
+    if (!this->history) {
+        std::fprintf(stderr, "gpu+b200: the history must not be null\n");
+        std::exit(-1);
+    }
+    this->tracking = true;
+    this->init(leapfrog);
+}
+
+void SimulationNBodyB200::init(const bool leapfrog)
+{
+    this->integrator = leapfrog ? B200NB_INTEGRATOR_LEAPFROG : B200NB_INTEGRATOR_MURB;
     // never touch this->allocator after the base constructor: the CLI passes a stack-local one (main.cpp:210,238)
     const float n = (float)this->getBodies()->getN();
     this->flopsPerIte = 20.f * n * n; // SimulationNBodyNaive.cpp:15
@@ -137,7 +159,10 @@ SimulationNBodyB200::SimulationNBodyB200(const BodiesAllocatorInterface<float> &
     this->b200Bodies->bind(this->G, this->soft, this->nGpus);
     this->allocatedBytes = this->bodies->getAllocatedBytes();
     const char *csv = std::getenv("MURB_B200_METRICS_CSV");
-    if (csv && *csv) this->metricsPath = csv;
+    if (csv && *csv) {
+        this->metricsPath = csv;
+        this->tracking = true;
+    }
     this->hostMirror = envInt("MURB_B200_HOST_MIRROR", 0) != 0;
 }
 
@@ -148,39 +173,59 @@ SimulationNBodyB200::~SimulationNBodyB200()
 
 void SimulationNBodyB200::saveMetricsToCSV(const std::string &filePath) const
 {
-    // same columns as SimulationHistory<T>::saveMetricsToCSV (SimulationHistory.cpp:103-122).  Upstream only ever fills
-    // in the energy; |L| and the density centre are computed here with the definitions of include/b200nb.h
-    std::ofstream out(filePath);
-    if (!out.is_open()) {
-        std::fprintf(stderr, "gpu+b200: cannot open metrics file '%s'\n", filePath.c_str());
-        return;
+    // the reference's own writer (SimulationHistory.cpp:103-122), on exactly the rows recorded so far.  Upstream only
+    // ever fills in the energy; |L| and the density centre carry the definitions of include/b200nb.h
+    SimulationHistory<double> rows((int)this->recorded);
+    for (size_t i = 0; i < this->recorded; i++) {
+        rows.setEnergyAt((int)i, this->history->getEnergyAt((int)i));
+        rows.setAngMomentumAt((int)i, this->history->getAngMomentumAt((int)i));
+        rows.setDensityCenterAt((int)i, this->history->getDensityCenterAt((int)i));
     }
-    out << "iteration,energy,ang_momentum,density_center_x,density_center_y,density_center_z\n";
-    out << std::setprecision(std::numeric_limits<double>::max_digits10);
-    for (size_t i = 0; i < this->energies.size(); i++)
-        out << i << ',' << this->energies[i] << ',' << this->angMomentums[i] << ',' << this->densityCenters[i][0] << ','
-            << this->densityCenters[i][1] << ',' << this->densityCenters[i][2] << '\n';
+    try {
+        rows.saveMetricsToCSV(filePath);
+    } catch (const std::exception &e) { // the reference throws when the file cannot be opened
+        std::fprintf(stderr, "gpu+b200: %s\n", e.what());
+    }
+}
+
+std::vector<double> SimulationNBodyB200::getEnergies() const
+{
+    const std::vector<double> &all = this->history->getAllEnergy();
+    return std::vector<double>(all.begin(), all.begin() + (long)this->recorded);
+}
+
+void SimulationNBodyB200::syncHistoryToDevice()
+{
+#ifdef USE_CUDA
+    if (auto gpu = std::dynamic_pointer_cast<GPUSimulationHistory<double>>(this->history)) gpu->copyToDevice();
+#endif
 }
 
 void SimulationNBodyB200::computeOneIteration()
 {
     b200nb_ctx *c = this->b200Bodies->context();
+    // like gpu+tracking, the metrics belong to the state the iteration starts from (...PropertyTracking.cu:121-133)
+    if (this->tracking) this->recordMetrics();
     check(b200nb_step(c, this->dt, this->integrator, 1), c, "b200nb_step");
     // main.cpp:353-371 joins the current device only; with several GPUs the others are joined here
     if (b200nb_n_local_gpus(c) > 1) check(b200nb_sync(c), c, "b200nb_sync");
     this->b200Bodies->invalidateDataSoA();
     if (this->hostMirror) (void)this->b200Bodies->getDataSoA(); // in place: the vectors never move, captured pointers stay valid
-    if (!this->metricsPath.empty()) this->recordMetrics();
 }
 
 void SimulationNBodyB200::recordMetrics()
 {
     const std::array<double, B200NB_N_METRICS> m = this->computeMetrics();
-    this->energies.push_back(m[B200NB_METRIC_ENERGY]);
-    this->angMomentums.push_back(std::sqrt(m[B200NB_METRIC_ANG_X] * m[B200NB_METRIC_ANG_X] +
-                                           m[B200NB_METRIC_ANG_Y] * m[B200NB_METRIC_ANG_Y] +
-                                           m[B200NB_METRIC_ANG_Z] * m[B200NB_METRIC_ANG_Z]));
-    this->densityCenters.push_back({m[B200NB_METRIC_DENSITY_X], m[B200NB_METRIC_DENSITY_Y], m[B200NB_METRIC_DENSITY_Z]});
+    // a caller-sized history (NIterations rows, main.cpp:247-248) is filled in place; otherwise it grows geometrically
+    // (GPUSimulationHistory reallocates its device mirror on every resize)
+    if ((int)this->recorded >= this->history->getNumIterations())
+        this->history->setNumIterations(std::max<int>(16, 2 * this->history->getNumIterations()));
+    const int k = (int)this->recorded++;
+    this->history->setEnergyAt(k, m[B200NB_METRIC_ENERGY]);
+    this->history->setAngMomentumAt(k, std::sqrt(m[B200NB_METRIC_ANG_X] * m[B200NB_METRIC_ANG_X] +
+                                              m[B200NB_METRIC_ANG_Y] * m[B200NB_METRIC_ANG_Y] +
+                                              m[B200NB_METRIC_ANG_Z] * m[B200NB_METRIC_ANG_Z]));
+    this->history->setDensityCenterAt(k, {m[B200NB_METRIC_DENSITY_X], m[B200NB_METRIC_DENSITY_Y], m[B200NB_METRIC_DENSITY_Z]});
 }
 
 std::array<double, B200NB_N_METRICS> SimulationNBodyB200::computeMetrics()

@@ -12,7 +12,9 @@
 //   MURB_B200_INTEGRATOR  "murb" (default) or "leapfrog"; the tag gpu+b200+leapfrog selects leapfrog too
 //   MURB_B200_METRICS_CSV path: track the total energy (what gpu+tracking does,
 //                         SimulationNBodyCUDAPropertyTracking.cu:217-369), |angular momentum| and the density centre
-//                         after every iteration and write them on destruction in the format of
+//                         of the state every iteration starts from (row k = state before iteration k, the reference's
+//                         convention: computeMetrics() precedes the update, ...PropertyTracking.cu:121-133) into a
+//                         SimulationHistory<double> and write it on destruction with the reference's own
 //                         SimulationHistory::saveMetricsToCSV (src/common/core/SimulationHistory.cpp:103-122)
 //   MURB_B200_HOST_MIRROR 1: copy positions and velocities back into the host SoA after every iteration.  The OpenGL
 //                         visualisers keep the raw host pointers they were given once (main.cpp:279-296) and read them
@@ -27,6 +29,7 @@
 
 #include "core/Bodies.hpp"
 #include "core/BodiesAllocator.hpp"
+#include "core/HistoryTrackingInterface.hpp"
 #include "core/SimulationNBodyInterface.hpp"
 
 #include "b200nb.h"
@@ -67,32 +70,41 @@ class B200BodiesAllocator : public BodiesAllocatorInterface<float> {
     const unsigned long randInit;
 };
 
-class SimulationNBodyB200 : public SimulationNBodyInterface<float> {
+// Like gpu+tracking (SimulationNBodyCUDAPropertyTracking.hpp:13) the class is also a history tracker: getHistory()
+// returns the reference's own container.  The base is the host-side HistoryTrackingInterface<double> so that the glue
+// stays free of CUDA; a caller may hand in any SimulationHistory<double>, in particular the GPUSimulationHistory<double>
+// the CLI makes for gpu+tracking (main.cpp:247-251) - syncHistoryToDevice() then refreshes its device mirror.
+class SimulationNBodyB200 : public SimulationNBodyInterface<float>, public HistoryTrackingInterface<double> {
   protected:
     std::shared_ptr<B200Bodies> b200Bodies;
     int integrator; // B200NB_INTEGRATOR_*
     int nGpus;
     accSoA_t<float> accSoA;
     bool hostMirror = false;       // refresh the host SoA after every iteration (visualiser hand-off)
-    std::string metricsPath;       // empty: no tracking
-    std::vector<double> energies;  // energies[i] = total energy after iteration i (fp64, like GPUSimulationHistory<double>)
-    std::vector<double> angMomentums;                  // |L| after iteration i (SimulationHistory.hpp:14)
-    std::vector<std::array<double, 3>> densityCenters; // SimulationHistory.hpp:15
+    bool tracking = false;         // record the metrics of the state every iteration starts from
+    std::string metricsPath;       // empty: no CSV on destruction
+    size_t recorded = 0;           // rows of the history filled so far
+    void init(const bool leapfrog);
     void recordMetrics();
 
   public:
     SimulationNBodyB200(const BodiesAllocatorInterface<float> &allocator, const float soft = 0.035f,
                         const bool leapfrog = false);
+    // the shape of SimulationNBodyCUDAPropertyTracking's constructor (...PropertyTracking.hpp:26-28): the caller owns
+    // the history and tracking is on
+    SimulationNBodyB200(const BodiesAllocatorInterface<float> &allocator, std::shared_ptr<SimulationHistory<double>> history,
+                        const float soft = 0.035f, const bool leapfrog = false);
     virtual ~SimulationNBodyB200();
     virtual void computeOneIteration();
-    const accSoA_t<float> &getAccSoA(); // accelerations of the last force pass (…PropertyTracking.cu:308-319)
+    const accSoA_t<float> &getAccSoA(); // accelerations of the last force pass (...PropertyTracking.cu:308-319)
     void computeAccelerationsOnly();    // force pass without integration (accuracy tests)
-    double computeEnergy();             // fp64 total energy (…PropertyTracking.cu:217-304 definition)
+    double computeEnergy();             // fp64 total energy (...PropertyTracking.cu:217-304 definition)
     const char *kernelName() const;
     std::array<double, B200NB_N_METRICS> computeMetrics(); // indices: B200NB_METRIC_* (include/b200nb.h)
-    const std::vector<double> &getEnergies() const { return energies; }
-    const std::vector<double> &getAllAngMomentum() const { return angMomentums; }
-    const std::vector<std::array<double, 3>> &getAllDensityCenter() const { return densityCenters; }
+    size_t getNumRecorded() const { return recorded; }
+    // rows [0, getNumRecorded()) of getHistory(): energy, |L|, density centre
+    std::vector<double> getEnergies() const;
+    void syncHistoryToDevice();         // GPUSimulationHistory only: copyToDevice(); otherwise a no-op
     void saveMetricsToCSV(const std::string &filePath) const;
 };
 

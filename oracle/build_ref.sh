@@ -4,7 +4,9 @@
 # (CMakeLists.txt:171) which this image lacks; the few sources on the path compile directly.
 #   1. libmurbref*.so   reference Bodies + cpu+naive/optim/simd/omp behind oracle/ref_wrap.cpp   (oracle pin, CPU baseline)
 #   2. murb_b200        reference main.cpp patched with the gpu+b200 branch + reference CPU and CUDA variants + the glue
-#   3. murb-test-b200   Catch2 runner: reference test harness conventions re-targeted at gpu+b200
+#   3. murb-test-b200   Catch2 runner: the reference's OWN test bodies (test_SimulationNBody.cpp, test_CUDABodies.cpp) with
+#                       only the class under test re-targeted at gpu+b200 by oracle/patch_test.py, the reference's
+#                       test_SimulationHistory.cu unchanged, and tests/catch2/test_B200.cpp (what the reference lacks)
 set -u
 REF=${1:-/root/reference}
 HERE=$(cd "$(dirname "$0")/.." && pwd)
@@ -55,12 +57,20 @@ LINK="-L$PKG/b200nb -lb200nb -Wl,-rpath,\$ORIGIN/../../nbody-eurohpc_b200/b200nb
 g++ "$OBJ/main_b200.o" $HOSTOBJS $objs $LINK -o "$OUT/murb_b200" || rc=1
 
 echo "== 3. murb-test-b200 (Catch2)"
-g++ $REFFLAGS -DUSE_CUDA $INC $CUDAINC -I"$PKG/glue" -I"$HERE/include" -I"$REF/lib/Catch2/include" \
-    -c "$HERE/tests/catch2/test_B200.cpp" -o "$OBJ/test_B200.o" || rc=1
+TESTINC="$INC $CUDAINC -I$PKG/glue -I$HERE/include -I$REF/lib/Catch2/include"
+python3 "$HERE/oracle/patch_test.py" "$REF" "$OUT" || rc=1
+g++ $REFFLAGS -DUSE_CUDA $TESTINC -c "$HERE/tests/catch2/test_B200.cpp" -o "$OBJ/test_B200.o" || rc=1
+for t in test_SimulationNBody_b200 test_CUDABodies_b200; do   # the reference's test bodies, class under test re-targeted
+  g++ $REFFLAGS -DUSE_CUDA $TESTINC -c "$OUT/$t.cpp" -o "$OBJ/$t.o" || rc=1
+done
+if stale "$OBJ/test_SimulationHistory.o" "$REF/src/test/implem/test_SimulationHistory.cu"; then   # unchanged
+  nvcc $NVFLAGS -I"$REF/lib/Catch2/include" -c "$REF/src/test/implem/test_SimulationHistory.cu" -o "$OBJ/test_SimulationHistory.o" 2>/dev/null || rc=1
+fi
 g++ $REFFLAGS -I"$REF/lib/Catch2/include" -c "$REF/src/test/main.cpp" -o "$OBJ/test_main.o" || rc=1
 TESTOBJS=""
 for o in $HOSTOBJS; do case "$o" in *ArgumentsReader*|*Nop.host.o|*SpheresVisuNo*) ;; *) TESTOBJS="$TESTOBJS $o";; esac; done
-g++ "$OBJ/test_main.o" "$OBJ/test_B200.o" $TESTOBJS $objs $LINK -o "$OUT/murb-test-b200" || rc=1
+g++ "$OBJ/test_main.o" "$OBJ/test_B200.o" "$OBJ/test_SimulationNBody_b200.o" "$OBJ/test_CUDABodies_b200.o" \
+    "$OBJ/test_SimulationHistory.o" $TESTOBJS $objs $LINK -o "$OUT/murb-test-b200" || rc=1
 ls -la "$OUT" | grep -v obj
 [ $rc = 0 ] && touch "$OUT/.stamp"
 exit $rc

@@ -17,7 +17,9 @@
 #include "SimulationNBodyB200.hpp"
 #include "SimulationNBodyNaive.hpp"
 #ifdef USE_CUDA
+#include "SimulationNBodyCUDAPropertyTracking.hpp"
 #include "SimulationNBodyCUDATileFullDevice.hpp"
+#include "core/SimulationHistoryGPU.hpp"
 #endif
 
 namespace {
@@ -231,20 +233,27 @@ TEST_CASE("gpu+b200 - metrics CSV", "[b200][metrics]")
         simu.setDt(3600);
         e0 = simu.computeEnergy();
         for (int it = 0; it < 5; it++) simu.computeOneIteration();
-        REQUIRE(simu.getEnergies().size() == 5);
-        for (double e : simu.getEnergies()) REQUIRE(std::abs((e - e0) / e0) < 1e-4);
+        REQUIRE(simu.getNumRecorded() == 5);
+        const std::vector<double> energies = simu.getEnergies();
+        REQUIRE(energies.size() == 5);
+        REQUIRE(energies[0] == e0); // row k = the state iteration k starts from (...PropertyTracking.cu:121-133)
+        for (double e : energies) REQUIRE(std::abs((e - e0) / e0) < 1e-4);
+        // the history is the reference's own container (SimulationHistory.hpp:11-49)
+        const std::shared_ptr<SimulationHistory<double>> h = simu.getHistory();
+        REQUIRE(h->getNumIterations() >= 5);
+        REQUIRE(h->getEnergyAt(3) == energies[3]);
         // the columns upstream leaves empty: |L| is conserved by kick-drift-kick (central pairwise forces), and the
         // potential-weighted centre of the galaxy scheme sits on the 2e24 kg body at the origin
-        REQUIRE(simu.getAllAngMomentum().size() == 5);
-        const double l0 = simu.getAllAngMomentum()[0];
+        const double l0 = h->getAngMomentumAt(0);
         REQUIRE(l0 > 0);
-        for (double l : simu.getAllAngMomentum()) REQUIRE(std::abs((l - l0) / l0) < 1e-5);
-        for (const auto &dc : simu.getAllDensityCenter())
-            for (int axis = 0; axis < 3; axis++) REQUIRE(std::abs(dc[axis]) < 2e7); // bodies live at 1e8..2e8 m
+        for (int k = 0; k < 5; k++) {
+            REQUIRE(std::abs((h->getAngMomentumAt(k) - l0) / l0) < 1e-5);
+            for (int axis = 0; axis < 3; axis++) REQUIRE(std::abs(h->getDensityCenterAt(k)[axis]) < 2e7); // bodies live at 1e8..2e8 m
+        }
         const auto m = simu.computeMetrics();
-        REQUIRE(m[B200NB_METRIC_ENERGY] == simu.getEnergies().back());
+        REQUIRE(std::abs((m[B200NB_METRIC_ENERGY] - e0) / e0) < 1e-4);
         REQUIRE(m[B200NB_METRIC_MASS] > 2e24);
-    } // destructor writes the file
+    } // destructor writes the file with the reference's saveMetricsToCSV
     unsetenv("MURB_B200_METRICS_CSV");
     std::ifstream in(path);
     REQUIRE(in.is_open());
@@ -262,6 +271,51 @@ TEST_CASE("gpu+b200 - metrics CSV", "[b200][metrics]")
     }
     REQUIRE(rows == 5);
 }
+
+#ifdef USE_CUDA
+// f2 pinned: the reference's own gpu+tracking (devComputeBodiesMetrics + cub::DeviceReduce::Sum into a
+// GPUSimulationHistory<double>, SimulationNBodyCUDAPropertyTracking.cu:217-304,333-364) against b200nb_metrics on the
+// same initial conditions, MUrB explicit integrator on both sides so the states coincide to fp32 rounding.  The
+// gpu+b200 side fills a caller-owned GPUSimulationHistory<double> through the same constructor shape.
+// (n stays below cub's single-tile limit on purpose: upstream sizes bufferForEnergy with sizeof(T) for Q = double,
+// ...PropertyTracking.cu:87, so the per-body doubles run past the allocation; the B200 objects are created first and
+// nothing else is allocated afterwards.)
+TEST_CASE("gpu+b200 - energy pinned to the reference's gpu+tracking", "[b200][metrics][pin]")
+{
+    for (const std::string scheme : {"galaxy", "random"}) {
+        const size_t n = scheme == "galaxy" ? 2048 : 3000;
+        const int nIte = 3;
+        const float soft = 2e+08, dt = 3600;
+        auto histB200 = std::make_shared<GPUSimulationHistory<double>>(nIte);
+        B200BodiesAllocator b200Alloc(n, scheme);
+        SimulationNBodyB200 b200(b200Alloc, histB200, soft, false);
+        b200.setDt(dt);
+        auto histRef = std::make_shared<GPUSimulationHistory<double>>(nIte);
+        CUDABodiesAllocator<float> refAlloc(n, scheme);
+        SimulationNBodyCUDAPropertyTracking<float, double> ref(refAlloc, histRef, soft);
+        ref.setDt(dt);
+        for (int it = 0; it < nIte; it++) {
+            ref.computeOneIteration(); // ends with history->copyFromDevice()
+            b200.computeOneIteration();
+        }
+        REQUIRE(b200.getNumRecorded() == (size_t)nIte);
+        REQUIRE(b200.getHistory().get() == histB200.get());
+        for (int it = 0; it < nIte; it++) {
+            const double eRef = ref.getHistory()->getEnergyAt(it), eB200 = histB200->getEnergyAt(it);
+            CAPTURE(scheme, it, eRef, eB200);
+            REQUIRE(eRef != 0.0);
+            REQUIRE(std::abs(eB200 - eRef) <= 1e-6 * std::abs(eRef));
+        }
+        // device mirror of the caller's GPUSimulationHistory: what a device-side consumer of gpu+tracking reads
+        b200.syncHistoryToDevice();
+        std::vector<double> dev(nIte);
+        REQUIRE(cudaMemcpy(dev.data(), histB200->getDevEnergy(), nIte * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess);
+        for (int it = 0; it < nIte; it++) REQUIRE(dev[it] == histB200->getEnergyAt(it));
+        std::cout << "  [pin] " << scheme << " n=" << n << ": E0 reference gpu+tracking " << std::setprecision(12)
+                  << ref.getHistory()->getEnergyAt(0) << ", gpu+b200 " << histB200->getEnergyAt(0) << std::endl;
+    }
+}
+#endif
 
 // What createVisu does (main.cpp:279-296): take the raw host pointers once, read them after every iteration without
 // ever calling getDataSoA() again.  With MURB_B200_HOST_MIRROR=1 those pointers must show the current state.

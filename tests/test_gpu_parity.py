@@ -544,12 +544,47 @@ def test_catch2_murb_test_b200():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-def test_patched_murb_cli():
-    """`murb -n 30000 -i 5 --nv --im gpu+b200 --gf`: the unmodified CLI loop + one registration branch."""
-    r = subprocess.run([_ref_bin("murb_b200"), "-n", "30000", "-i", "5", "--nv", "--im", "gpu+b200", "--gf"],
-                       capture_output=True, text=True, timeout=600)
+def test_reference_own_test_bodies_on_gpu_b200():
+    """The reference's own murb-test sources (test_SimulationNBody.cpp: `n-body - Correctness`, the four sections with the
+    reference's loop and tolerances; test_CUDABodies.cpp: `CUDABodies`) with only the class under test re-targeted at
+    gpu+b200 by oracle/patch_test.py, and its test_SimulationHistory.cu unchanged."""
+    exe = _ref_bin("murb-test-b200")
+    for name, min_assertions in (("n-body - Correctness", 4 * 3 * 2048), ("CUDABodies", 4 * 4000), ("[GPUSimulationHistory]", 5)):
+        r = subprocess.run([exe, name], capture_output=True, text=True, timeout=900)
+        print(r.stdout[-600:])
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        m = __import__("re").search(r"All tests passed \((\d+) assertions? in (\d+) test cases?\)", r.stdout)
+        assert m and int(m.group(1)) >= min_assertions, r.stdout[-500:]
+
+
+def test_energy_pinned_to_reference_gpu_tracking():
+    """f2: b200nb_metrics' energy against the reference's own devComputeBodiesMetrics + GPUSimulationHistory<double>
+    (SimulationNBodyCUDAPropertyTracking.cu:217-304,333-364) at the same states, rel <= 1e-6 (Catch2 case [pin])."""
+    r = subprocess.run([_ref_bin("murb-test-b200"), "[pin]"], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-1500:])
+    assert r.returncode == 0 and "All tests passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("tag", ["gpu+b200", "gpu+b200+leapfrog"])
+def test_patched_murb_cli(tag, tmp_path):
+    """`murb -n 30000 -i 5 --nv --im <tag> --gf`: the unmodified CLI loop + one registration branch, with the metrics
+    CSV (the gpu+tracking analogue) written through the reference's own SimulationHistory::saveMetricsToCSV."""
+    csv = tmp_path / "metrics.csv"
+    env = dict(os.environ, MURB_B200_METRICS_CSV=str(csv))
+    env.pop("MURB_B200_NGPUS", None)
+    r = subprocess.run([_ref_bin("murb_b200"), "-n", "30000", "-i", "5", "--nv", "--im", tag, "--gf"],
+                       capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "gpu+b200" in r.stdout and "Gflop/s" in r.stdout
+    assert tag in r.stdout and "Gflop/s" in r.stdout
+    lines = csv.read_text().strip().split("\n")
+    assert lines[0] == "iteration,energy,ang_momentum,density_center_x,density_center_y,density_center_z"
+    rows = [[float(x) for x in l.split(",")] for l in lines[1:]]
+    assert [int(r_[0]) for r_ in rows] == [0, 1, 2, 3, 4]
+    e0 = rows[0][1]
+    assert e0 < 0  # a bound system
+    drift = max(abs((r_[1] - e0) / e0) for r_ in rows)
+    assert drift < (1e-5 if tag.endswith("leapfrog") else 1e-2), drift
+    assert all(r_[2] > 0 for r_ in rows)  # |L|: the column upstream leaves at 0
 
 
 @pytest.mark.parametrize("exchange", ["nccl", "p2p"])
