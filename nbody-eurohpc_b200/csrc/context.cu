@@ -89,9 +89,13 @@ const KernelVariant g_variants[] = {
     // default first; chosen from the B200 sweep in profiles/ (tools/kbench)
     // 8 targets per thread and only 2 warps per scheduler: the operand-reuse cache keeps hitting while one warp keeps
     // issuing, which is what gets the accumulate FFMA2 triples back to 2 cycles
-    VARIANT_SK("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, 2, 9.5),
+    VARIANT_SK("pk_t128_r8_tj2_st3_cta_u1_mb2", 128, 8, 2, 3, 1, 2, 9.53),
     // small systems: 256-target tiles and 1-block stages give enough CTAs to fill 148 SMs below N ~ 30k
     VARIANT_SK("pk_t128_r2_tj1_st3_cta_u2_mb4", 128, 2, 1, 3, 2, 4, 9.2),
+    // one-warp CTAs, 8 per SM: the R = 8 inner loop on 256-target tiles.  Same rate as the default at large N (9.53),
+    // ahead of it when a rank has few tiles (sharded runs: 25 088 targets x 200k sources 9.40 vs 9.34 vs 9.19 for the
+    // R = 2 variant, profiles/r02_kbench_cluster_smalltiles.txt)
+    VARIANT("pk_t32_r8_tj2_st2_cta_u1_mb8", 32, 8, 2, 2, 1, false, 1, 8, 9.53),
     VARIANT("pk_t128_r8_tj4_st2_cta_u1_mb2", 128, 8, 4, 2, 1, false, 1, 2, 9.5),
     VARIANT("pk_t256_r8_tj2_st3_cta_u1_mb1", 256, 8, 2, 3, 1, false, 1, 1, 9.5),
     VARIANT("pk_t256_r2_tj2_st3_cta_u2_mb3", 256, 2, 2, 3, 1, false, 2, 3, 9.0),
@@ -274,25 +278,22 @@ ChunkPlan plan_for(const KernelVariant &kv, uint64_t n, uint64_t L, int n_sms, i
                        (uint32_t)n_ranks, max_rows_for((L + ti - 1) / ti * ti, n_ranks), (uint32_t)(2 * kv.tjb));
 }
 
-// Between the large-tile default and the small-tile variant, take the one the planner expects to finish first:
-// modelled pass time = (CTA-block-times) x (interactions per CTA-block) / (per-CTA rate = SM rate / resident CTAs).
+// Between the large-tile default, the one-warp R = 8 variant and the small R = 2 variant, take the one the planner
+// expects to finish first (plan.hpp: choose_variant_index).  Sharded runs list the 256-target R = 8 variant first: with
+// few tiles per rank its finer tile granularity wins and the model cannot tell it from the default.
 int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
 {
     cudaDeviceProp prop;
     CU(c, cudaSetDevice(device)); // the occupancy query below answers for the current device
     CU(c, cudaGetDeviceProperties(&prop, device));
-    const KernelVariant *cands[2] = {&g_variants[0], &g_variants[1]};
-    double best_t = 1e300;
+    const KernelVariant *cands[3] = {&g_variants[0], &g_variants[2], &g_variants[1]};
+    if (c->n_ranks > 1) std::swap(cands[0], cands[1]);
     *out = cands[0];
-    for (const KernelVariant *kv : cands) {
-        int occ = 0;
-        CU(c, cudaFuncSetAttribute(kv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv->smem));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kv->fn, kv->threads, kv->smem));
-        if (occ < 1) continue;
-        const char *mode = getenv("B200NB_MODE");
-        double t;
-        if (kv->fn_sk && mode && !strcmp(mode, "sk")) {
-            // stream-K: every CTA gets ceil(U/G) (tile x block) units; a unit is TI x 128 interactions at SM rate / occ
+    const char *mode = getenv("B200NB_MODE");
+    if (mode && !strcmp(mode, "sk")) {
+        // stream-K: every CTA gets ceil(U/G) (tile x block) units; a unit is TI x 128 interactions at SM rate / occ
+        double best_t = 1e300;
+        for (const KernelVariant *kv : {&g_variants[0], &g_variants[1]}) {
             int occ_sk = 0;
             CU(c, cudaFuncSetAttribute(kv->fn_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv->smem_sk));
             CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sk, kv->fn_sk, kv->threads, kv->smem_sk));
@@ -300,13 +301,25 @@ int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
             const uint64_t G = (uint64_t)prop.multiProcessorCount * occ_sk;
             const uint64_t ti = (uint64_t)kv->threads * kv->r;
             const uint64_t U = ((c->L + ti - 1) / ti) * (c->total_pad_hint / BLK);
-            t = (double)((U + G - 1) / G) * (double)ti * (double)occ_sk / kv->int_per_clk_sm;
-        } else {
-            const ChunkPlan p = plan_for(*kv, c->n, c->L, prop.multiProcessorCount, occ, c->n_ranks);
-            t = p.cta_block_times * (double)(kv->threads * kv->r) * (double)occ / kv->int_per_clk_sm;
+            const double t = (double)((U + G - 1) / G) * (double)ti * (double)occ_sk / kv->int_per_clk_sm;
+            if (t < best_t) { best_t = t; *out = kv; }
         }
-        if (t < best_t) { best_t = t; *out = kv; }
+        return B200NB_OK;
     }
+    VariantShape shapes[3];
+    uint32_t max_rows[3];
+    for (int i = 0; i < 3; ++i) {
+        const KernelVariant *kv = cands[i];
+        int occ = 0;
+        CU(c, cudaFuncSetAttribute(kv->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kv->smem));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kv->fn, kv->threads, kv->smem));
+        shapes[i] = VariantShape{(uint32_t)kv->threads, (uint32_t)kv->r, (uint32_t)kv->tjb, (uint32_t)std::max(occ, 0), kv->int_per_clk_sm};
+        const uint64_t ti = (uint64_t)kv->threads * kv->r;
+        max_rows[i] = max_rows_for((c->L + ti - 1) / ti * ti, c->n_ranks);
+    }
+    const int pick = choose_variant_index(shapes, 3, c->L, source_blocks(c->n, c->L, c->n_ranks) / (uint32_t)c->n_ranks,
+                                          (uint32_t)prop.multiProcessorCount, (uint32_t)c->n_ranks, max_rows);
+    if (pick >= 0) *out = cands[pick];
     return B200NB_OK;
 }
 

@@ -130,6 +130,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  : "memory");
 }
 
+// thread-block cluster helpers (distributed shared memory)
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float from the shared memory of CTA `rank` of this cluster at the same offset as local address `addr`
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t addr, uint32_t rank)
+{
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------- launch args
 struct ForceArgs {
     const float *src;            // blocked bodies the sources are read from (full replicated array)
@@ -338,11 +353,18 @@ __device__ __forceinline__ void block_scalar(const float *__restrict__ sb, const
 // WARP_PRIVATE each warp owns its stages and barriers (no CTA-wide barrier in the loop)
 // U            unroll of the 4-source inner step
 // MINB         min resident CTAs per SM for __launch_bounds__
-template <int THREADS, int R, int TJB, int ST, int MATH, bool WARP_PRIVATE, int U, int MINB>
+// CL           thread-block cluster size along the chunk axis (launch with cluster dims (1, CL, 1); gridDim.y % CL == 0).
+//              CL > 1: the CL CTAs of a cluster work on CL consecutive chunks of the SAME target tile and add their
+//              partial sums over distributed shared memory in a fixed order (fp64, rounded once), so the launch writes
+//              one partial row per cluster instead of one per CTA: CL times less HBM/L2 traffic for the partial rows
+//              and CL times fewer rows for the integrator to add, still deterministic.
+template <int THREADS, int R, int TJB, int ST, int MATH, bool WARP_PRIVATE, int U, int MINB, int CL = 1>
 __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
 {
     constexpr int TI = THREADS * R;
     static_assert(TI % BLK == 0, "target tile must cover whole blocks");
+    static_assert(CL == 1 || (!WARP_PRIVATE && (size_t)ST * TJB * BLK_BYTES >= (size_t)3 * TI * 4 && (3 * TI) % CL == 0),
+                  "cluster reduction reuses the drained pipeline stages as a [3][TI] float buffer");
     constexpr int GROUPS = WARP_PRIVATE ? THREADS / 32 : 1;
     constexpr int STAGE_FLOATS = TJB * BLK_FLOATS;
 
@@ -451,13 +473,41 @@ __global__ void __launch_bounds__(THREADS, MINB) force_kernel(const ForceArgs a)
         }
     }
 
-    const size_t row = (size_t)c * 3;
+    if constexpr (CL == 1) {
+        const size_t row = (size_t)c * 3;
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-        const size_t il = (size_t)blockIdx.x * TI + (size_t)k * THREADS + threadIdx.x;
-        a.partial[(row + 0) * a.tgt_stride + il] = mx[k];
-        a.partial[(row + 1) * a.tgt_stride + il] = my[k];
-        a.partial[(row + 2) * a.tgt_stride + il] = mz[k];
+        for (int k = 0; k < R; ++k) {
+            const size_t il = (size_t)blockIdx.x * TI + (size_t)k * THREADS + threadIdx.x;
+            a.partial[(row + 0) * a.tgt_stride + il] = mx[k];
+            a.partial[(row + 1) * a.tgt_stride + il] = my[k];
+            a.partial[(row + 2) * a.tgt_stride + il] = mz[k];
+        }
+    } else {
+        // cluster reduction over distributed shared memory.  red[comp][off], off = target offset inside the tile.
+        __syncthreads(); // every thread is done reading the pipeline stages
+        float *red = stages;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int off = k * THREADS + (int)threadIdx.x;
+            red[off] = mx[k];
+            red[TI + off] = my[k];
+            red[2 * TI + off] = mz[k];
+        }
+        cluster_sync_all(); // all CL buffers are complete and visible cluster-wide
+        uint32_t crank;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        constexpr int COLS = 3 * TI / CL; // columns of the [3][TI] buffer this CTA finishes
+        const size_t row = (size_t)(c / CL) * 3;
+        const uint32_t red_u32 = smem_u32(red);
+        for (int idx = (int)threadIdx.x; idx < COLS; idx += THREADS) {
+            const int col = (int)crank * COLS + idx;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < CL; ++q) s += (double)ld_dsmem_f32(red_u32 + 4u * (uint32_t)col, (uint32_t)q); // fixed order
+            const int comp = col / TI, off = col - comp * TI;
+            a.partial[(row + comp) * a.tgt_stride + (size_t)blockIdx.x * TI + off] = (float)s;
+        }
+        cluster_sync_all(); // nobody leaves while a peer may still read its shared memory
     }
 
     if (a.dbg != nullptr && threadIdx.x == 0) {

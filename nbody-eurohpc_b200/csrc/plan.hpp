@@ -59,4 +59,41 @@ inline ChunkPlan plan_chunks(uint32_t n_itiles, uint32_t blocks_per_slice, uint3
     return best;
 }
 
+// ---- choosing between kernel variants (host only) ----
+// Shape of a force-kernel variant as the planner sees it.  rate = measured steady-state interactions / clk / SM.
+struct VariantShape {
+    uint32_t threads, r, tjb, occ; // occ: resident CTAs per SM (cudaOccupancyMaxActiveBlocksPerMultiprocessor); 0 = cannot run
+    double rate;
+};
+
+// Modelled duration of one force pass of a rank (arbitrary units, comparable between variants):
+// (CTA-block-times of the plan) x (interactions per CTA-block) / (per-CTA rate = SM rate / resident CTAs).
+inline double modelled_pass_time(const VariantShape &v, uint64_t L, uint32_t blocks_per_slice, uint32_t n_sms, uint32_t n_ranks,
+                                 uint32_t max_rows)
+{
+    const uint32_t ti = v.threads * v.r;
+    const ChunkPlan p = plan_chunks((uint32_t)((L + ti - 1) / ti), blocks_per_slice, n_sms * v.occ, n_ranks, max_rows, 2 * v.tjb);
+    return p.cta_block_times * (double)ti * (double)v.occ / v.rate;
+}
+
+// Index of the variant expected to finish first.  Candidates are listed in order of preference: a later one replaces
+// the incumbent only if the model expects it to be clearly faster - by more than 0.5 % between variants with the same
+// inner loop (same R), by more than 2.5 % when the inner loop changes (whole-wave quantisation in the model is worth
+// that much; measured: at 25 088 targets x 200k sources the model favours R = 2 by 1.7 % and R = 8 is 2.3 % faster).
+inline int choose_variant_index(const VariantShape *v, int count, uint64_t L, uint32_t blocks_per_slice, uint32_t n_sms,
+                                uint32_t n_ranks, const uint32_t *max_rows, double *times = nullptr)
+{
+    int best = -1;
+    double best_t = 1e300;
+    for (int i = 0; i < count; ++i) {
+        if (times) times[i] = -1.0;
+        if (v[i].occ < 1) continue;
+        const double t = modelled_pass_time(v[i], L, blocks_per_slice, n_sms, n_ranks, max_rows[i]);
+        if (times) times[i] = t;
+        const double margin = (best >= 0 && v[i].r != v[best].r) ? 0.975 : 0.995;
+        if (best < 0 || t < margin * best_t) { best = i; best_t = t; }
+    }
+    return best;
+}
+
 } // namespace b200nb

@@ -19,6 +19,20 @@ int main(int argc, char **argv)
     if (argv[1][0] == 'p') {  // p n_itiles blocks_per_slice slots n_ranks max_rows min_blocks
         ChunkPlan p = plan_chunks(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]));
         printf("{\"k\": %u, \"waves\": %u, \"eff\": %.6f, \"t\": %.3f}\n", p.n_chunks, p.waves, p.wave_efficiency, p.cta_block_times);
+    } else if (argv[1][0] == 'v') {  // v L blocks_per_slice n_ranks  (B200: 148 SMs; candidates in the library's order)
+        const uint64_t L = strtoull(argv[2], 0, 10);
+        const uint32_t bps = atoi(argv[3]), ranks = atoi(argv[4]);
+        VariantShape big{128, 8, 2, 2, 9.53}, warp{32, 8, 2, 8, 9.53}, small{128, 2, 1, 4, 9.2};
+        VariantShape v[3] = {big, warp, small};
+        if (ranks > 1) { v[0] = warp; v[1] = big; }
+        uint32_t max_rows[3];
+        for (int i = 0; i < 3; ++i) {
+            const uint64_t ti = (uint64_t)v[i].threads * v[i].r, lp = (L + ti - 1) / ti * ti;
+            max_rows[i] = (uint32_t)std::max<uint64_t>(ranks, std::min<uint64_t>(256, (1ull << 30) / (12ull * lp)));
+        }
+        double t[3];
+        const int pick = choose_variant_index(v, 3, L, bps, 148, ranks, max_rows, t);
+        printf("{\"pick\": %d, \"threads\": %u, \"r\": %u, \"t\": [%.1f, %.1f, %.1f]}\n", pick, v[pick].threads, v[pick].r, t[0], t[1], t[2]);
     } else {                  // s n_itiles nb G : every unit is owned by exactly one CTA, rows per tile are consistent
         const uint32_t n_itiles = atoi(argv[2]), nb = atoi(argv[3]), G = atoi(argv[4]);
         const uint64_t U = (uint64_t)n_itiles * nb;
@@ -75,3 +89,15 @@ def test_stream_k_ownership_and_rows(harness, n_itiles, nb, G):
     assert 1 <= r["max_rows"] <= G
     if n_itiles >= G:
         assert r["max_rows"] <= 2   # a tile is split across at most two CTAs when there are more tiles than CTAs
+
+
+@pytest.mark.parametrize("n,ranks,expect", [(200000, 1, (128, 8)), (1000000, 1, (128, 8)), (4194304, 1, (128, 8)), (2048, 1, (128, 2)),
+                                            (8192, 1, (128, 2)), (16384, 1, (128, 2)), (200000, 8, (32, 8)), (4194304, 8, (32, 8)),
+                                            (1000000, 8, (32, 8)), (50000, 2, (32, 8)), (4000, 2, (128, 2)), (100000, 1, (128, 8))])
+def test_variant_choice(harness, n, ranks, expect):
+    """Large single-GPU systems keep the 1024-target R = 8 default, murb-test sizes take the small R = 2 tiles, sharded
+    runs the one-warp R = 8 variant (measured: profiles/r02_kbench_cluster_smalltiles.txt)."""
+    L = (-(-n // ranks) + 255) // 256 * 256
+    blocks_per_slice = -(-n // 128) if ranks == 1 else L // 128
+    v = harness("v", L, blocks_per_slice, ranks)
+    assert (v["threads"], v["r"]) == expect, v

@@ -165,6 +165,7 @@ struct Problem {
 struct Variant {
     std::string name;
     int threads, r, tjb, st, packed, warp_private, u, minb;
+    int cl = 1; // thread-block cluster size along the chunk axis
     std::function<void(const ForceArgs &, dim3)> launch;
     const void *fn;
     size_t smem;
@@ -172,7 +173,7 @@ struct Variant {
 
 static std::vector<Variant> g_variants;
 
-template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MINB> static void reg_variant(size_t pad_smem = 0)
+template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MINB, int CL = 1> static void reg_variant(size_t pad_smem = 0)
 {
     Variant v;
     char nm[128];
@@ -180,13 +181,25 @@ template <int THREADS, int R, int TJB, int ST, int MATH, bool WP, int U, int MIN
              WP ? "warp" : "cta", U, MINB);
     v.name = nm;
     if (pad_smem) v.name += "_pad" + std::to_string(pad_smem / 1024) + "k";
-    v.threads = THREADS; v.r = R; v.tjb = TJB; v.st = ST; v.packed = MATH; v.warp_private = WP; v.u = U; v.minb = MINB;
-    auto k = force_kernel<THREADS, R, TJB, ST, MATH, WP, U, MINB>;
+    if (CL > 1) v.name += "_cl" + std::to_string(CL);
+    v.threads = THREADS; v.r = R; v.tjb = TJB; v.st = ST; v.packed = MATH; v.warp_private = WP; v.u = U; v.minb = MINB; v.cl = CL;
+    auto k = force_kernel<THREADS, R, TJB, ST, MATH, WP, U, MINB, CL>;
     v.fn = (const void *)k;
     v.smem = force_smem_bytes<THREADS, R, TJB, ST, WP>() + pad_smem; // padding only lowers the occupancy
     v.launch = [k, smem = v.smem](const ForceArgs &a, dim3 grid) {
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, THREADS, smem>>>(a);
+        if (CL == 1) {
+            k<<<grid, THREADS, smem>>>(a);
+        } else {
+            if (CL > 8) CK(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = CL; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, k, a));
+        }
     };
     g_variants.push_back(v);
 }
@@ -195,6 +208,23 @@ static void register_all()
 {
 #ifdef KBENCH_ONLY_DEFAULT // schedule-knob experiments: -DKBENCH_ONLY_DEFAULT -DB200NB_KNOB_...=x builds in seconds
     reg_variant<128, 8, 2, 3, 1, false, 1, 2>();
+    return;
+#endif
+#ifdef KBENCH_ROUND2 // round-2 experiments only: cluster reduction of the chunk partials, small R=8 tiles
+    reg_variant<128, 8, 2, 3, 1, false, 1, 2>();
+    reg_variant<128, 8, 2, 3, 1, false, 1, 2, 2>();
+    reg_variant<128, 8, 2, 3, 1, false, 1, 2, 4>();
+    reg_variant<128, 8, 2, 3, 1, false, 1, 2, 8>();
+    reg_variant<128, 8, 2, 3, 1, false, 1, 2, 16>();
+    reg_variant<64, 8, 2, 3, 1, false, 1, 4>();
+    reg_variant<64, 8, 1, 3, 1, false, 1, 4>();
+    reg_variant<64, 8, 1, 3, 1, false, 1, 4, 4>();
+    reg_variant<32, 8, 1, 3, 1, false, 1, 8>();
+    reg_variant<32, 8, 1, 2, 1, false, 1, 8>();
+    reg_variant<32, 8, 2, 2, 1, false, 1, 8>();
+    reg_variant<32, 8, 1, 3, 1, false, 1, 8, 4>();
+    reg_variant<128, 2, 1, 3, 1, false, 2, 4>();
+    reg_variant<128, 2, 1, 3, 1, false, 2, 4, 4>();
     return;
 #endif
     //            THR  R TJB ST MATH  WP    U MINB      MATH: 0 scalar, 1 packed, 2 packed + scalar accumulate, 3 packed + shuffle broadcast
@@ -286,13 +316,14 @@ static void make_problem(Problem &p, size_t n, int sms)
 
 int main(int argc, char **argv)
 {
-    size_t n = 200000;
+    size_t n = 200000, n_targets = 0; // n_targets > 0: only the first n_targets bodies are targets (a rank's slice)
     int reps = 3, micro = 1, chunks_override = 0, check = 1;
     std::string two_level;
     std::string filter, outpath = "gpurun_out/kbench.jsonl";
     for (int i = 1; i < argc; ++i) {
         auto arg = [&](const char *k) { return !strcmp(argv[i], k) && i + 1 < argc; };
         if (arg("--n")) n = strtoull(argv[++i], 0, 10);
+        else if (arg("--targets")) n_targets = strtoull(argv[++i], 0, 10);
         else if (arg("--reps")) reps = atoi(argv[++i]);
         else if (arg("--micro")) micro = atoi(argv[++i]);
         else if (arg("--filter")) filter = argv[++i];
@@ -359,10 +390,24 @@ int main(int argc, char **argv)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.fn, v.threads, v.smem));
         if (occ < 1) { printf("%-34s cannot launch (occ 0)\n", v.name.c_str()); continue; }
         const uint32_t ti = v.threads * v.r;
-        const uint32_t n_itiles = (uint32_t)(p.n_pad / ti);
+        const size_t tgt_total = n_targets ? std::min(p.n_pad, (n_targets + ti - 1) / ti * ti) : p.n_pad;
+        const uint32_t n_itiles = (uint32_t)(tgt_total / ti);
         const uint32_t n_blocks = (uint32_t)(p.n_pad / BLK);
         ChunkPlan plan = plan_chunks(n_itiles, n_blocks, (uint32_t)(sms * occ), 1u, (uint32_t)p.partial_rows, (uint32_t)(2 * v.tjb));
         if (chunks_override > 0) plan.n_chunks = std::min<uint32_t>((uint32_t)chunks_override, (uint32_t)p.partial_rows); // never past the allocated rows
+        if (v.cl > 1) plan.n_chunks = std::max<uint32_t>(v.cl, plan.n_chunks / v.cl * v.cl); // whole clusters along the chunk axis
+        const uint32_t out_rows = plan.n_chunks / v.cl; // partial rows the launch writes
+        int max_clusters = -1;
+        if (v.cl > 1) {
+            if (v.cl > 8) CK(cudaFuncSetAttribute(v.fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(n_itiles, plan.n_chunks); qc.blockDim = dim3(v.threads); qc.dynamicSmemBytes = v.smem;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = v.cl; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, v.fn, &qc) != cudaSuccess) { max_clusters = -2; (void)cudaGetLastError(); }
+        }
         ForceArgs a{};
         a.src = p.d_bodies; a.tgt = p.d_bodies; a.partial = p.d_partial;
         a.tgt_blk0 = 0; a.tgt_stride = (uint32_t)p.n_pad; a.tgt_count = (uint32_t)p.n_pad;
@@ -418,13 +463,14 @@ int main(int argc, char **argv)
         // accuracy: sum partial rows on the host in fp64 for the checked targets
         double maxrel = -1;
         if (check) {
-            std::vector<float> hp((size_t)plan.n_chunks * 3 * p.n_pad);
+            std::vector<float> hp((size_t)out_rows * 3 * p.n_pad);
             CK(cudaMemcpy(hp.data(), p.d_partial, hp.size() * 4, cudaMemcpyDeviceToHost));
             maxrel = 0;
             for (size_t c = 0; c < p.check_idx.size(); ++c) {
                 const size_t i = p.check_idx[c];
+                if (i >= tgt_total) continue;
                 double ax = 0, ay = 0, az = 0;
-                for (uint32_t s = 0; s < plan.n_chunks; ++s) {
+                for (uint32_t s = 0; s < out_rows; ++s) {
                     ax += hp[((size_t)s * 3 + 0) * p.n_pad + i];
                     ay += hp[((size_t)s * 3 + 1) * p.n_pad + i];
                     az += hp[((size_t)s * 3 + 2) * p.n_pad + i];
@@ -435,12 +481,14 @@ int main(int argc, char **argv)
                 maxrel = std::max(maxrel, num / den);
             }
         }
-        const double inter = (double)p.n_pad * (double)p.n_pad; // padded pairs are computed too
+        const double inter = (double)tgt_total * (double)p.n_pad; // padded pairs are computed too
         const double gints = inter / (best_ms * 1e-3) / 1e9;
-        const double useful = (double)n * (double)n / (best_ms * 1e-3) / 1e9;
+        const double useful = (double)(n_targets ? std::min(n_targets, n) : n) * (double)n / (best_ms * 1e-3) / 1e9;
         const double ipc = mhz > 0 ? inter / (best_ms * 1e-3) / (mhz * 1e6) / sms : 0;
-        printf("%-34s %4d %5.1f %3d %6u %6u %9.3f %9.1f %8.0f %8.3f %9.2e\n", v.name.c_str(), fa.numRegs, v.smem / 1024.0,
+        printf("%-34s %4d %5.1f %3d %6u %6u %9.3f %9.1f %8.0f %8.3f %9.2e", v.name.c_str(), fa.numRegs, v.smem / 1024.0,
                occ, plan.n_chunks, plan.waves, best_ms, useful, mhz, ipc, maxrel);
+        if (v.cl > 1) printf("  rows=%u max_active_clusters=%d (x%d CTAs = %d of %d slots)", out_rows, max_clusters, v.cl, max_clusters * v.cl, sms * occ);
+        printf("\n");
         if (jf) {
             fprintf(jf,
                     "{\"variant\":\"%s\",\"n\":%zu,\"regs\":%d,\"smem\":%zu,\"occ\":%d,\"chunks\":%u,\"waves\":%u,\"ms\":%.4f,"
