@@ -278,16 +278,16 @@ ChunkPlan plan_for(const KernelVariant &kv, uint64_t n, uint64_t L, int n_sms, i
                        (uint32_t)n_ranks, max_rows_for((L + ti - 1) / ti * ti, n_ranks), (uint32_t)(2 * kv.tjb));
 }
 
-// Between the large-tile default, the one-warp R = 8 variant and the small R = 2 variant, take the one the planner
-// expects to finish first (plan.hpp: choose_variant_index).  Sharded runs list the 256-target R = 8 variant first: with
-// few tiles per rank its finer tile granularity wins and the model cannot tell it from the default.
+// Between the one-warp R = 8 variant (256-target tiles), the 4-warp R = 8 variant (1024-target tiles) and the small R = 2
+// variant, take the one the planner expects to finish first (plan.hpp: choose_variant_index).  The one-warp variant is
+// listed first: it matches the 4-warp one at large N (N = 200k inside bench.py: 14.52 vs 14.56 ms per launch, with 56
+// instead of 74 partial rows; profiles/r02_ncu_force_kernel_*.txt) and its finer tiles win when a rank has few of them.
 int choose_variant(b200nb_ctx *c, int device, const KernelVariant **out)
 {
     cudaDeviceProp prop;
     CU(c, cudaSetDevice(device)); // the occupancy query below answers for the current device
     CU(c, cudaGetDeviceProperties(&prop, device));
-    const KernelVariant *cands[3] = {&g_variants[0], &g_variants[2], &g_variants[1]};
-    if (c->n_ranks > 1) std::swap(cands[0], cands[1]);
+    const KernelVariant *cands[3] = {&g_variants[2], &g_variants[0], &g_variants[1]};
     *out = cands[0];
     const char *mode = getenv("B200NB_MODE");
     if (mode && !strcmp(mode, "sk")) {

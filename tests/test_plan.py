@@ -23,8 +23,7 @@ int main(int argc, char **argv)
         const uint64_t L = strtoull(argv[2], 0, 10);
         const uint32_t bps = atoi(argv[3]), ranks = atoi(argv[4]);
         VariantShape big{128, 8, 2, 2, 9.53}, warp{32, 8, 2, 8, 9.53}, small{128, 2, 1, 4, 9.2};
-        VariantShape v[3] = {big, warp, small};
-        if (ranks > 1) { v[0] = warp; v[1] = big; }
+        VariantShape v[3] = {warp, big, small};
         uint32_t max_rows[3];
         for (int i = 0; i < 3; ++i) {
             const uint64_t ti = (uint64_t)v[i].threads * v[i].r, lp = (L + ti - 1) / ti * ti;
@@ -91,12 +90,12 @@ def test_stream_k_ownership_and_rows(harness, n_itiles, nb, G):
         assert r["max_rows"] <= 2   # a tile is split across at most two CTAs when there are more tiles than CTAs
 
 
-@pytest.mark.parametrize("n,ranks,expect", [(200000, 1, (128, 8)), (1000000, 1, (128, 8)), (4194304, 1, (128, 8)), (2048, 1, (128, 2)),
+@pytest.mark.parametrize("n,ranks,expect", [(200000, 1, (32, 8)), (1000000, 1, (32, 8)), (4194304, 1, (32, 8)), (2048, 1, (128, 2)),
                                             (8192, 1, (128, 2)), (16384, 1, (128, 2)), (200000, 8, (32, 8)), (4194304, 8, (32, 8)),
-                                            (1000000, 8, (32, 8)), (50000, 2, (32, 8)), (4000, 2, (128, 2)), (100000, 1, (128, 8))])
+                                            (1000000, 8, (32, 8)), (50000, 2, (32, 8)), (4000, 2, (128, 2)), (100000, 1, (32, 8))])
 def test_variant_choice(harness, n, ranks, expect):
-    """Large single-GPU systems keep the 1024-target R = 8 default, murb-test sizes take the small R = 2 tiles, sharded
-    runs the one-warp R = 8 variant (measured: profiles/r02_kbench_cluster_smalltiles.txt)."""
+    """Large systems and sharded runs take the one-warp R = 8 variant (256-target tiles), murb-test sizes the small R = 2
+    tiles (measured: profiles/r02_kbench_cluster_smalltiles.txt, profiles/r02_ncu_force_kernel_200k_t32.txt)."""
     L = (-(-n // ranks) + 255) // 256 * 256
     blocks_per_slice = -(-n // 128) if ranks == 1 else L // 128
     v = harness("v", L, blocks_per_slice, ranks)
