@@ -337,7 +337,7 @@ def boundary_targets(n, L, world, extra=40, seed=11):
     return np.unique(np.clip(np.array(idx, dtype=np.int64), 0, n - 1)).astype(np.uint64)
 
 
-def parity_check(b200nb, ctx, bodies, n, world, rank):
+def parity_check(b200nb, ctx, bodies, n, world, rank, scheme):
     """After the timed region: one more force pass on the positions the last exchange published, state + accelerations
     back to the host (collective), and on rank 0 the fp64 all-pairs oracle on the sampled targets (O(targets x N))."""
     ctx.accel()
@@ -350,14 +350,32 @@ def parity_check(b200nb, ctx, bodies, n, world, rank):
     moved = dict(bodies)
     moved.update({k: state[k] for k in ("qx", "qy", "qz")})
     t0 = time.perf_counter()
-    a64 = pyoracle.load().accel_f64(moved, idx)
+    a64 = np.stack(pyoracle.load().accel_f64(moved, idx))
     ii = idx.astype(np.int64)
-    err = pyoracle.max_rel_err(a64, [a[ii] for a in acc])
+    got = np.stack([a[ii] for a in acc]).astype(np.float64)
+    err_each = np.linalg.norm(got - a64, axis=0) / np.linalg.norm(a64, axis=0)
     finite = all(bool(np.all(np.isfinite(state[k]))) for k in ("qx", "qy", "qz", "vx", "vy", "vz"))
-    return {"max_rel_err": err, "tol": 1e-5, "targets": int(len(idx)), "ok": bool(err <= 1e-5 and finite), "state_finite": finite,
-            "what": "max |a - a_fp64| / |a_fp64| of a force pass on the final positions of this run, fp64 all-pairs oracle "
-                    "(oracle/nbody_oracle.c: oracle_accel_f64) on targets straddling every slice boundary + both ends + random",
-            "oracle_s": time.perf_counter() - t0}
+    # Body 0 of the galaxy scheme is the 2e24 kg central mass (Bodies.cpp:158-214): its acceleration is the residual of N
+    # nearly cancelling pulls (|a_0| ~ 1e-3 of everyone else's, condition number sum|t_j| / |sum t_j| ~ 1e3), so its
+    # relative error is ~1e3 x the per-term rounding (measured 5e-7 at the initial positions, 5e-6..9e-6 once it has left
+    # the origin; every other target stays below 2e-7, tools/parity_probe.py).  It is reported on its own, against a
+    # bound that scales with that conditioning, so that the 1e-5 bound on everyone else stays meaningful.
+    central = scheme == "galaxy"
+    regular = (ii != 0) if central else np.ones(len(ii), bool)
+    err = float(err_each[regular].max())
+    out = {"max_rel_err": err, "tol": 1e-5, "targets": int(regular.sum()), "ok": bool(err <= 1e-5 and finite), "state_finite": finite,
+           "median_rel_err": float(np.median(err_each[regular])),
+           "what": "max |a - a_fp64| / |a_fp64| of a force pass on the final positions of this run, fp64 all-pairs oracle "
+                   "(oracle/nbody_oracle.c: oracle_accel_f64) on targets straddling every slice boundary + both ends + random",
+           "oracle_s": time.perf_counter() - t0}
+    if central:
+        e0 = float(err_each[ii == 0][0])
+        out["central_body"] = {"rel_err": e0, "tol": 1e-4, "abs_a": float(np.linalg.norm(a64[:, ii == 0])),
+                               "typical_abs_a": float(np.median(np.linalg.norm(a64[:, regular], axis=0))),
+                               "why": "body 0 = the 2e24 kg central mass: |a_0| is the residual of N cancelling pulls, ~1e-3 of a typical "
+                                      "|a| (condition number ~1e3), so it gets its own bound"}
+        out["ok"] = bool(out["ok"] and e0 <= 1e-4)
+    return out
 
 
 def timed_steps_single_gpu(b200nb, scheme, n, steps, warmup):
@@ -526,7 +544,7 @@ def run_b200_arm(args, rank, world, local_rank):
     e2e_value = interactions_per_step * e2e_steps / e2e_s / 1e9
 
     # ---- parity of this very run (all ranks: the downloads are collective)
-    parity = parity_check(b200nb, ctx, bodies, n, world, rank)
+    parity = parity_check(b200nb, ctx, bodies, n, world, rank, args.scheme)
 
     if rank != 0:
         ctx.close()
