@@ -156,6 +156,7 @@ struct b200nb_ctx {
     std::string kname;                  // variant name (+ "+sk" in stream-K mode)
     bool stream_k = false;              // stream-K decomposition instead of the (tile x chunk) grid
     bool p2p = false;                   // exchange = peer stores from the integrator (in-process multi-GPU) instead of NCCL
+    bool merge_launches = true;         // one force launch when the exchange has already landed at enqueue time (B200NB_SPLIT_LAUNCHES=1: never)
     uint32_t sk_grid = 0;               // CTAs per stream-K launch (resident slots)
     uint32_t sk_rows_own = 0, sk_rows_rem = 0;
     std::vector<Shard> shards;
@@ -348,11 +349,13 @@ int prof_start(b200nb_ctx *c, Shard &s)
 {
     if (s.prof.size() >= 2 * PROF_RING)
         if (int rc = prof_drain(c, s)) return rc;
-    cudaEvent_t e[2];
-    for (auto &ev : e) {
-        if (!s.prof_free.empty()) { ev = s.prof_free.back(); s.prof_free.pop_back(); }
-        else CU(c, cudaEventCreate(&ev));
+    while (s.prof_free.size() < 2) {
+        cudaEvent_t ev;
+        CU(c, cudaEventCreate(&ev));
+        s.prof_free.push_back(ev);
     }
+    cudaEvent_t e[2];
+    for (auto &ev : e) { ev = s.prof_free.back(); s.prof_free.pop_back(); }
     s.prof.push_back(e[0]);
     s.prof.push_back(e[1]);
     CU(c, cudaEventRecord(e[0], s.s_compute));
@@ -466,6 +469,7 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
         if (want_sk && !c->stream_k) { c->err = "B200NB_MODE=sk: variant has no stream-K kernel"; return bail(B200NB_EINVAL); }
     }
     c->kname = std::string(c->kv->name) + (c->stream_k ? "+sk" : "");
+    c->merge_launches = getenv("B200NB_SPLIT_LAUNCHES") == nullptr;
     if (c->stream_k) {
         const uint32_t ti = c->kv->threads * c->kv->r;
         const uint32_t n_itiles = (uint32_t)(c->Lp / ti), nbs = (uint32_t)(c->L / BLK);
@@ -512,6 +516,23 @@ int create_common(b200nb_ctx **out, uint64_t n, float G, float soft, int n_ranks
     }
     *out = c;
     return B200NB_OK;
+}
+
+// Have the remote slices of the current positions already landed on shard `s` (host-side query, no waiting)?  True when
+// the caller steps synchronously (the CLI joins the device after every iteration, main.cpp:356-368): the exchange of
+// the previous step is long over by the time the next force pass is enqueued, there is nothing left to overlap, and
+// the pass can be ONE launch over all chunks instead of own-slice + remote launches with a tail each.
+bool remote_positions_landed(b200nb_ctx *c, Shard &s)
+{
+    bool ready = true;
+    if (!c->p2p) {
+        ready = cudaEventQuery(s.ev_gathered) == cudaSuccess;
+    } else {
+        for (auto &o : c->shards)
+            if (&o != &s) ready = ready && cudaEventQuery(o.ev_pushed) == cudaSuccess;
+    }
+    if (!ready) (void)cudaGetLastError(); // cudaErrorNotReady is an answer, not a fault
+    return ready;
 }
 
 // the compute stream of `s` may not read remote slices before they have landed
@@ -589,6 +610,9 @@ int enqueue_force(b200nb_ctx *c)
         };
         if (c->n_ranks == 1) {
             if (int rc = launch(0, c->rows)) return rc;
+        } else if (c->merge_launches && remote_positions_landed(c, s)) {
+            if (int rc = wait_remote_positions(c, s)) return rc; // already complete: orders the stream, costs nothing
+            if (int rc = launch(0, c->rows)) return rc;          // same chunks, same rows: bit-identical to the split form
         } else {
             if (int rc = launch(0, c->k_per_slice)) return rc; // own slice: resident, overlaps the exchange
             if (int rc = wait_remote_positions(c, s)) return rc;

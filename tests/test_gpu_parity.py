@@ -429,6 +429,31 @@ def test_virtual_shards_reupload_and_host_accel(b200, oracle):
         assert np.array_equal(res[0][k].view(np.uint32), res[1][k].view(np.uint32)), k
 
 
+def test_merged_force_launch_is_bit_identical(b200, oracle, monkeypatch):
+    """When a sharded context is stepped synchronously (what the murb CLI does) the exchange has landed before the next
+    force pass is enqueued and the pass is ONE launch over all chunks; stepped asynchronously, or with
+    B200NB_SPLIT_LAUNCHES=1, it is the own-slice launch + the remote launch.  Same chunks, same rows, same bits."""
+    n = 40000
+    d = oracle.init_bodies("galaxy", n)
+    res = {}
+    for mode in ("merged", "split"):
+        if mode == "split":
+            monkeypatch.setenv("B200NB_SPLIT_LAUNCHES", "1")
+        with b200.Context(n, G_F32, SOFT, devices=[0, 0, 0, 0]) as ctx:
+            ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+            before = ctx.launch_count
+            for _ in range(6):
+                ctx.step(DT, 0, 1)
+                ctx.sync()          # synchronous stepping: every exchange is over before the next enqueue
+            launches = ctx.launch_count - before
+            res[mode] = (ctx.download_state(), ctx.download_accel(), launches)
+    assert res["merged"][2] == 6 * 4 * 2 and res["split"][2] == 6 * 4 * 3   # (force [+ force] + integrate) per shard per step
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(res["merged"][0][k].view(np.uint32), res["split"][0][k].view(np.uint32)), k
+    for a, b in zip(res["merged"][1], res["split"][1]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_virtual_shards_reject_nccl(b200, monkeypatch):
     monkeypatch.setenv("B200NB_EXCHANGE", "nccl")
     with pytest.raises(b200.B200Error) as e:
