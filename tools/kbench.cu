@@ -222,6 +222,11 @@ static void register_all()
     reg_variant<32, 8, 1, 3, 1, false, 1, 8>();
     reg_variant<32, 8, 1, 2, 1, false, 1, 8>();
     reg_variant<32, 8, 2, 2, 1, false, 1, 8>();
+    reg_variant<32, 8, 2, 3, 1, false, 1, 8>();
+    reg_variant<32, 8, 4, 2, 1, false, 1, 8>();
+    reg_variant<32, 8, 4, 3, 1, false, 1, 8>();
+    reg_variant<32, 8, 8, 2, 1, false, 1, 8>();
+    reg_variant<64, 8, 4, 2, 1, false, 1, 4>();
     reg_variant<32, 8, 1, 3, 1, false, 1, 8, 4>();
     reg_variant<128, 2, 1, 3, 1, false, 2, 4>();
     reg_variant<128, 2, 1, 3, 1, false, 2, 4, 4>();
