@@ -528,8 +528,12 @@ bool remote_positions_landed(b200nb_ctx *c, Shard &s)
     if (!c->p2p) {
         ready = cudaEventQuery(s.ev_gathered) == cudaSuccess;
     } else {
-        for (auto &o : c->shards)
-            if (&o != &s) ready = ready && cudaEventQuery(o.ev_pushed) == cudaSuccess;
+        for (auto &o : c->shards) {
+            if (&o == &s || !ready) continue;
+            if (o.device != s.device) (void)cudaSetDevice(o.device); // query an event on the device that owns it
+            ready = cudaEventQuery(o.ev_pushed) == cudaSuccess;
+        }
+        (void)cudaSetDevice(s.device);
     }
     if (!ready) (void)cudaGetLastError(); // cudaErrorNotReady is an answer, not a fault
     return ready;

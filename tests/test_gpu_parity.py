@@ -84,9 +84,10 @@ def test_accel_vs_reference_golden(b200, oracle, golden, scheme, n):
     assert max_rel_err(ref, acc) <= 2e-5
 
 
-@pytest.mark.parametrize("scheme,n", [("galaxy", 200000), ("random", 200000), ("galaxy", 1000000), ("random", 1048576)])
+@pytest.mark.parametrize("scheme,n", [("galaxy", 200000), ("random", 200000), ("galaxy", 1000000), ("random", 1048576),
+                                      ("galaxy", 4194304)])
 def test_accel_full_size_properties(b200, oracle, scheme, n):
-    """BASELINE sizes, where an N^2 CPU oracle is out of reach: (1) 192 sampled targets vs the fp64 oracle (O(192 N)),
+    """BASELINE sizes (configs[1], [3] and the 4M strong-scaling workload), where an N^2 CPU oracle is out of reach: (1) 192 sampled targets vs the fp64 oracle (O(192 N)),
     (2) total momentum rate sum_i m_i a_i = 0, (3) doubling every mass doubles every acceleration bit-exactly,
     (4) a second run is bit-identical (fixed-order partial sums)."""
     d = oracle.init_bodies(scheme, n)
