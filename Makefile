@@ -12,8 +12,15 @@ REF       ?= /root/reference
 
 all: lib oracle
 
+# the default force-kernel variant with its hot loop re-ordered after ptxas (tools/sass_resched.py + the committed order)
+RESCHED_VARIANT := 32, 8, 2, 2, 1, false, 1, 8, 1
+RESCHED_ORDER   := $(PKG)/csrc/resched/pk_t32_r8_tj2_st2_cta_u1_mb8.order.json
+RESCHED_INC     := $(PKG)/csrc/generated/force_resched_cubin.inc
+$(RESCHED_INC): tools/sass_resched.py $(RESCHED_ORDER) $(PKG)/csrc/force_sm100.cuh $(PKG)/csrc/plan.hpp
+	mkdir -p $(dir $@) build/resched && python3 tools/sass_resched.py "$(RESCHED_VARIANT)" build/resched/default.cubin --order-in $(RESCHED_ORDER) --emit-header $@
+
 lib: $(LIB)
-$(LIB): $(PKG)/csrc/context.cu $(PKG)/csrc/host_ic.cpp $(PKG)/csrc/force_sm100.cuh $(PKG)/csrc/integrate_sm100.cuh $(PKG)/csrc/plan.hpp include/b200nb.h
+$(LIB): $(PKG)/csrc/context.cu $(PKG)/csrc/host_ic.cpp $(PKG)/csrc/force_sm100.cuh $(PKG)/csrc/integrate_sm100.cuh $(PKG)/csrc/plan.hpp include/b200nb.h $(RESCHED_INC)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/context.cu $(PKG)/csrc/host_ic.cpp -ldl
 
 oracle: oracle/liboracle.so
@@ -27,7 +34,7 @@ ref:
 
 kbench: build/kbench
 build/kbench: tools/kbench.cu $(PKG)/csrc/force_sm100.cuh $(PKG)/csrc/plan.hpp
-	mkdir -p build && $(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ tools/kbench.cu
+	mkdir -p build && $(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ tools/kbench.cu -L/usr/local/cuda/lib64/stubs -lcuda
 
 clean:
 	rm -f $(LIB) oracle/liboracle.so build/kbench; rm -rf oracle/_ref

@@ -564,7 +564,7 @@ def run_b200_arm(args, rank, world, local_rank):
     traffic, traffic_src = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
         t = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
-        if t["workload_bodies"] == n and world == 1 and t.get("kernel_name") in (None, ctx.kernel_name):
+        if t["workload_bodies"] == n and world == 1 and ctx.kernel_name.startswith(t.get("kernel_name", "")):
             traffic = t["dram_bytes_per_launch"]
             traffic_src = "constant from the committed ncu --set full capture of this workload (" + t["source"] + "), not measured by this run"
     except Exception:

@@ -239,6 +239,31 @@ def test_graph_replay_is_bit_identical(b200, oracle, integrator, monkeypatch):
         assert np.array_equal(ref[k].view(np.uint32), got[k].view(np.uint32)), k
 
 
+# ------------------------------------------------------------------------------------------------ re-ordered cubin
+@pytest.mark.parametrize("scheme,n,devices", [("galaxy", 200000, [0]), ("random", 50001, [0]), ("galaxy", 120000, [0, 0, 0])])
+def test_reordered_kernel_is_bit_identical(b200, oracle, scheme, n, devices, monkeypatch):
+    """The default variant is launched from a cubin whose hot loop was re-ordered after ptxas (tools/sass_resched.py; same
+    instructions, registers and arithmetic).  It must agree BIT FOR BIT with the kernel ptxas scheduled
+    (B200NB_NO_RESCHED=1), for the force pass and through a few steps, also on sharded contexts."""
+    d = oracle.init_bodies(scheme, n)
+    res = {}
+    for mode in ("resched", "ptxas"):
+        if mode == "ptxas":
+            monkeypatch.setenv("B200NB_NO_RESCHED", "1")
+        with b200.Context(n, G_F32, SOFT, devices=devices) as ctx:
+            res[mode + "_name"] = ctx.kernel_name
+            ctx.upload(d["qx"], d["qy"], d["qz"], d["m"], d["vx"], d["vy"], d["vz"])
+            ctx.accel()
+            acc = ctx.download_accel()
+            ctx.step(DT, 1, 3)
+            res[mode] = (acc, ctx.download_state())
+    assert res["resched_name"] == res["ptxas_name"] + "+resched", (res["resched_name"], res["ptxas_name"])
+    for a, b in zip(res["resched"][0], res["ptxas"][0]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for k in ("qx", "qy", "qz", "vx", "vy", "vz"):
+        assert np.array_equal(res["resched"][1][k].view(np.uint32), res["ptxas"][1][k].view(np.uint32)), k
+
+
 # ------------------------------------------------------------------------------------------------ API behaviour
 def test_state_errors(b200, oracle):
     ctx = b200.Context(100, G_F32, SOFT)

@@ -2,6 +2,7 @@
 // Development tool, not part of the shipped library. Prints a table and writes JSON lines.
 //   kbench [--n N] [--reps K] [--micro 0|1] [--filter substr] [--out file] [--chunks S] [--check 0|1]
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +10,8 @@
 #include <functional>
 #include <string>
 #include <vector>
+
+#include <cuda.h>
 
 #include "../nbody-eurohpc_b200/csrc/force_sm100.cuh"
 #include "../nbody-eurohpc_b200/csrc/plan.hpp"
@@ -324,6 +327,8 @@ int main(int argc, char **argv)
     size_t n = 200000, n_targets = 0; // n_targets > 0: only the first n_targets bodies are targets (a rank's slice)
     int reps = 3, micro = 1, chunks_override = 0, check = 1;
     std::string two_level;
+    std::string cubin_path, cubin_kernel; // --cubin: a post-processed cubin of the variant selected by --filter (tools/sass_resched.py)
+    long serve_offset = -1;               // --serve OFFSET: evaluate candidate loop encodings read from stdin (hardware-in-the-loop search)
     std::string filter, outpath = "gpurun_out/kbench.jsonl";
     for (int i = 1; i < argc; ++i) {
         auto arg = [&](const char *k) { return !strcmp(argv[i], k) && i + 1 < argc; };
@@ -336,6 +341,9 @@ int main(int argc, char **argv)
         else if (arg("--chunks")) chunks_override = atoi(argv[++i]);
         else if (arg("--check")) check = atoi(argv[++i]);
         else if (arg("--two-level")) two_level = argv[++i]; // "Sbig,frac_small,ratio": decreasing chunk sizes, see below
+        else if (arg("--cubin")) cubin_path = argv[++i];
+        else if (arg("--cubin-kernel")) cubin_kernel = argv[++i];
+        else if (arg("--serve")) serve_offset = strtol(argv[++i], 0, 0);
     }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -494,6 +502,125 @@ int main(int argc, char **argv)
                occ, plan.n_chunks, plan.waves, best_ms, useful, mhz, ipc, maxrel);
         if (v.cl > 1) printf("  rows=%u max_active_clusters=%d (x%d CTAs = %d of %d slots)", out_rows, max_clusters, v.cl, max_clusters * v.cl, sms * occ);
         printf("\n");
+        if (!cubin_path.empty() && serve_offset >= 0) {
+            // Evaluation server for tools/sass_resched.py --hw-search.  Protocol, one request per line on stdin:
+            //   "T <hex>"  patch <hex> (the loop's new encoding) at the offset, load, time `reps` launches -> "ms <best>"
+            //   "V <hex>"  the same plus a bitwise comparison with the built-in kernel's partial sums -> "ms <best> diffs <n>"
+            //   "Q"        quit
+            std::vector<float> ref((size_t)out_rows * 3 * p.n_pad);
+            CK(cudaMemcpy(ref.data(), p.d_partial, ref.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<unsigned char> image;
+            {
+                FILE *f = fopen(cubin_path.c_str(), "rb");
+                if (!f) { fprintf(stderr, "cannot open %s\n", cubin_path.c_str()); return 6; }
+                fseek(f, 0, SEEK_END);
+                image.resize(ftell(f));
+                fseek(f, 0, SEEK_SET);
+                if (fread(image.data(), 1, image.size(), f) != image.size()) return 6;
+                fclose(f);
+            }
+            ForceArgs a2 = a;
+            a2.dbg = nullptr;
+            void *params[1] = {&a2};
+            std::vector<float> got(ref.size());
+            static char line[1 << 16];
+            printf("ready\n");
+            fflush(stdout);
+            while (fgets(line, sizeof line, stdin)) {
+                if (line[0] == 'Q') break;
+                const bool verify = line[0] == 'V';
+                const char *hex = line + 2;
+                size_t nb = 0;
+                while (isxdigit((unsigned char)hex[2 * nb]) && isxdigit((unsigned char)hex[2 * nb + 1])) ++nb;
+                if ((size_t)serve_offset + nb > image.size()) { printf("err size\n"); fflush(stdout); continue; }
+                for (size_t q = 0; q < nb; ++q) {
+                    unsigned v2;
+                    sscanf(hex + 2 * q, "%2x", &v2);
+                    image[serve_offset + q] = (unsigned char)v2;
+                }
+                CUmodule mod;
+                CUfunction fn;
+                if (cuModuleLoadData(&mod, image.data()) != CUDA_SUCCESS) { printf("err load\n"); fflush(stdout); continue; }
+                if (cuModuleGetFunction(&fn, mod, cubin_kernel.c_str()) != CUDA_SUCCESS) { printf("err func\n"); fflush(stdout); cuModuleUnload(mod); continue; }
+                cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)v.smem);
+                if (verify) CK(cudaMemset(p.d_partial, 0xff, ref.size() * 4));
+                float best2 = 1e30f;
+                bool failed = false;
+                for (int r = 0; r < reps + 1 && !failed; ++r) {
+                    CK(cudaEventRecord(e0));
+                    if (cuLaunchKernel(fn, grid.x, grid.y, 1, v.threads, 1, 1, (unsigned)v.smem, 0, params, nullptr) != CUDA_SUCCESS) failed = true;
+                    CK(cudaEventRecord(e1));
+                    if (cudaDeviceSynchronize() != cudaSuccess) failed = true;
+                    float ms = 0.f;
+                    if (!failed) { CK(cudaEventElapsedTime(&ms, e0, e1)); if (r > 0) best2 = std::min(best2, ms); }
+                }
+                if (failed) { printf("err run\n"); fflush(stdout); return 7; } // the context is gone
+                if (verify) {
+                    CK(cudaMemcpy(got.data(), p.d_partial, got.size() * 4, cudaMemcpyDeviceToHost));
+                    size_t diff = 0; // only the columns this launch writes: the first tgt_total targets of every row
+                    for (size_t rr = 0; rr < (size_t)out_rows * 3; ++rr)
+                        for (size_t col = 0; col < tgt_total; ++col) diff += memcmp(&ref[rr * p.n_pad + col], &got[rr * p.n_pad + col], 4) != 0;
+                    printf("ms %.5f diffs %zu\n", best2, diff);
+                } else {
+                    printf("ms %.5f\n", best2);
+                }
+                fflush(stdout);
+                cuModuleUnload(mod);
+            }
+            return 0;
+        }
+        if (!cubin_path.empty()) {
+            // the same launch through a post-processed cubin (driver API): must be bit-identical, may be faster
+            std::vector<float> ref((size_t)out_rows * 3 * p.n_pad);
+            CK(cudaMemcpy(ref.data(), p.d_partial, ref.size() * 4, cudaMemcpyDeviceToHost));
+            CUmodule mod;
+            CUfunction fn;
+            auto DR = [](CUresult r, const char *what) {
+                if (r != CUDA_SUCCESS) { const char *s = nullptr; cuGetErrorString(r, &s); fprintf(stderr, "driver error in %s: %s\n", what, s ? s : "?"); exit(4); }
+            };
+            DR(cuModuleLoad(&mod, cubin_path.c_str()), "cuModuleLoad");
+            DR(cuModuleGetFunction(&fn, mod, cubin_kernel.c_str()), "cuModuleGetFunction");
+            DR(cuFuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)v.smem), "cuFuncSetAttribute");
+            CK(cudaMemset(p.d_partial, 0xff, ref.size() * 4));
+            ForceArgs a2 = a;
+            a2.dbg = nullptr;
+            void *params[1] = {&a2};
+            auto launch2 = [&]() { DR(cuLaunchKernel(fn, grid.x, grid.y, 1, v.threads, 1, 1, (unsigned)v.smem, 0, params, nullptr), "cuLaunchKernel"); };
+            launch2();
+            cudaError_t se2 = cudaDeviceSynchronize();
+            if (se2 != cudaSuccess) { printf("%-34s CUBIN FAILED: %s\n", v.name.c_str(), cudaGetErrorString(se2)); return 5; }
+            std::vector<float> got(ref.size());
+            CK(cudaMemcpy(got.data(), p.d_partial, got.size() * 4, cudaMemcpyDeviceToHost));
+            size_t diff = 0; // only the columns this launch writes: the first tgt_total targets of every row
+            for (size_t rr = 0; rr < (size_t)out_rows * 3; ++rr)
+                for (size_t col = 0; col < tgt_total; ++col) diff += memcmp(&ref[rr * p.n_pad + col], &got[rr * p.n_pad + col], 4) != 0;
+            float best2 = 1e30f;
+            for (int r = 0; r < reps; ++r) {
+                CK(cudaEventRecord(e0));
+                launch2();
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+                float ms;
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                best2 = std::min(best2, ms);
+            }
+            // and the built-in one again, interleaved, so that both see the same clocks
+            float best1 = 1e30f;
+            for (int r = 0; r < reps; ++r) {
+                CK(cudaEventRecord(e0));
+                v.launch(a2, grid);
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+                float ms;
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                best1 = std::min(best1, ms);
+            }
+            printf("  cubin %s: %zu of %zu partial sums differ bitwise; %.3f ms vs built-in %.3f ms -> %+.2f %%\n", cubin_path.c_str(), diff,
+                   ref.size(), best2, best1, 100.0 * (best1 / best2 - 1.0));
+            if (jf) fprintf(jf, "{\"cubin\":\"%s\",\"variant\":\"%s\",\"n\":%zu,\"bitwise_diffs\":%zu,\"ms_cubin\":%.4f,\"ms_builtin\":%.4f}\n",
+                            cubin_path.c_str(), v.name.c_str(), n, diff, best2, best1);
+            cuModuleUnload(mod);
+        }
         if (jf) {
             fprintf(jf,
                     "{\"variant\":\"%s\",\"n\":%zu,\"regs\":%d,\"smem\":%zu,\"occ\":%d,\"chunks\":%u,\"waves\":%u,\"ms\":%.4f,"

@@ -1,0 +1,633 @@
+#!/usr/bin/env python3
+"""Post-ptxas rescheduling of the force kernel's hot loop (experiment; see DESIGN.md §3.1 "cycle accounting").
+
+ptxas fixes the register allocation and emits the 233-instruction loop in an order that costs ~27.1 clk per packed source
+pair where the instruction mix allows 25.0 (tools/cycle_accounting.py).  This tool takes the cubin of one force_kernel
+instantiation, rebuilds the loop's dependence graph from the SASS (register RAW / WAR / WAW, scoreboard barriers, the
+in-order completion ptxas relies on for MUFU pairs, loop-carried edges), searches for a better ORDER of the same
+instructions with simulated annealing under the register-read cost model measured on B200
+(profiles/r01_microbench_pipes.txt, r01_microbench_mufu_coissue.txt), regenerates the scheduling control fields (stall
+counts, operand-reuse flags; barriers and yield stay with their instructions) and writes a patched cubin.  The arithmetic
+is untouched, so the patched kernel must be BIT-IDENTICAL to the original: tools/kbench --cubin checks exactly that.
+
+    python tools/sass_resched.py "32, 8, 2, 2, 1, false, 1, 8, 1" out.cubin [--iters 300000] [--seed 7]
+"""
+import argparse
+import math
+import os
+import random
+import re
+import subprocess
+import sys
+from collections import defaultdict
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(REPO, "nbody-eurohpc_b200", "csrc", "force_sm100.cuh")
+FMA2 = ("FADD2", "FMUL2", "FFMA2")
+
+
+# ------------------------------------------------------------------------------------------------ SASS parsing
+def parse_sass(text):
+    lines, ins, i = text.split("\n"), [], 0
+    while i < len(lines):
+        m = re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(.*?);\s+/\* (0x[0-9a-f]{16}) \*/", lines[i])
+        if m and i + 1 < len(lines):
+            m2 = re.match(r"\s+/\* (0x[0-9a-f]{16}) \*/", lines[i + 1])
+            if m2:
+                ins.append({"addr": int(m.group(1), 16), "text": re.sub(r"\s+", " ", m.group(2).strip()),
+                            "lo": int(m.group(3), 16), "hi": int(m2.group(1), 16)})
+                i += 2
+                continue
+        i += 1
+    return ins
+
+
+def ctrl(hi):
+    c = hi >> 41
+    return {"stall": c & 0xf, "yld": (c >> 4) & 1, "wr": (c >> 5) & 7, "rd": (c >> 8) & 7, "wait": (c >> 11) & 0x3f, "reuse": (c >> 17) & 0xf}
+
+
+def set_ctrl(hi, stall, reuse):
+    c = hi >> 41
+    c = (c & ~0xf) | (stall & 0xf)
+    c = (c & ~(0xf << 17)) | ((reuse & 0xf) << 17)
+    return (hi & ((1 << 41) - 1)) | (c << 41)
+
+
+def operands(t):
+    """(opcode, destination resources, [(slot, source resources)]) for the instruction forms that occur in the loop"""
+    op = t.split()[0]
+    rest = t[len(op):].strip()
+    args = [a.strip() for a in rest.split(",")] if rest else []
+
+    def regs(a, wide=None):
+        a = a.replace(".reuse", "")
+        m = re.search(r"(?<![A-Za-z])(U?R)(\d+)", a)
+        if not m:
+            m2 = re.search(r"(UP\d)", a)
+            return {m2.group(1)} if m2 else set()
+        base, pre = int(m.group(2)), m.group(1)
+        n = wide or (2 if "F32x2" in a else 1)
+        return {f"{pre}{base + k}" for k in range(n)}
+
+    if op.startswith("LDS.128"):
+        return op, regs(args[0], 4), [(0, regs(args[1]))]
+    if op.startswith(FMA2):
+        return op, regs(args[0], 2), [(k, regs(a)) for k, a in enumerate(args[1:])]
+    if op.startswith("MUFU"):
+        return op, regs(args[0]), [(0, regs(args[1]))]
+    if op.startswith("UISETP"):
+        return op, {"UP0"}, [(0, regs(args[2]))]
+    if op.startswith("UIADD3"):
+        return op, regs(args[0]), [(0, regs(args[3]))]
+    if op.startswith("UMOV"):
+        return op, regs(args[0]), [(0, regs(args[1]))]
+    if op.startswith("BRA"):
+        return op, set(), [(0, {"UP0"} if "UP0" in t else {"UP1"})]
+    raise ValueError("unexpected instruction in the hot loop: " + t)
+
+
+def find_loop(ins):
+    """the backward-branch region with the most FFMA2"""
+    by_addr = {x["addr"]: k for k, x in enumerate(ins)}
+    best = None
+    for k, x in enumerate(ins):
+        m = re.match(r"BRA(?:\.U)? .*?(0x[0-9a-f]+)$", x["text"])
+        if m and int(m.group(1), 16) <= x["addr"] and int(m.group(1), 16) in by_addr:
+            s = by_addr[int(m.group(1), 16)]
+            n = sum("FFMA2" in y["text"] for y in ins[s:k + 1])
+            if best is None or n > best[0]:
+                best = (n, s, k)
+    return best[1], best[2]
+
+
+# ------------------------------------------------------------------------------------------------ dependence graph
+def is_fma2(x):
+    return x["op"].startswith(FMA2)
+
+
+def is_var(x):  # variable latency: completion is signalled through a scoreboard barrier
+    return x["op"].startswith(("MUFU", "LDS"))
+
+
+def build_edges(body):
+    """edges (producer index, consumer index, min issue distance in cycles, carried) taken from the ORIGINAL cyclic order"""
+    n = len(body)
+
+    def lat_raw(p, c):
+        if is_fma2(p):
+            return 5 if c["op"].startswith("MUFU") else 4       # minimum distances ptxas itself uses in this loop
+        if is_var(p):
+            return 2                                            # real latency is enforced by the covering barrier wait
+        return 7                                                # uniform datapath
+
+    def lat_war(p, c):
+        if p["op"].startswith("MUFU"):
+            return 12                                           # ptxas: >= 9 without a read barrier
+        if not is_fma2(p) and not is_var(p):
+            return 7
+        return 2
+
+    acc = []
+    for x in body:
+        rd, wr = set(), set(x["d"])
+        for _, rs in x["s"]:
+            rd |= rs
+        c = x["c"]
+        for b in (c["wr"], c["rd"]):
+            if b != 7:
+                wr.add(f"SB{b}")
+        for b in range(6):
+            if c["wait"] >> b & 1:
+                rd.add(f"SB{b}")
+        acc.append((rd, wr))
+    edges = set()
+    lastw, readers = {}, defaultdict(list)
+    for rep in range(2):
+        for j in range(n):
+            rd, wr = acc[j]
+            for r in rd:
+                if r in lastw:
+                    i, ri = lastw[r]
+                    if not (rep == 1 and ri == 1):
+                        edges.add((i, j, 2 if r.startswith("SB") else lat_raw(body[i], body[j]), rep - ri))
+            for r in wr:
+                for (i, ri) in readers[r]:
+                    if i != j and not (rep == 1 and ri == 1):
+                        edges.add((i, j, 2 if r.startswith("SB") else lat_war(body[i], body[j]), rep - ri))
+                if r in lastw:
+                    i, ri = lastw[r]
+                    if i != j and not (rep == 1 and ri == 1):
+                        edges.add((i, j, 2, rep - ri))
+                readers[r] = []
+                lastw[r] = (j, rep)
+            for r in rd:
+                readers[r].append((j, rep))
+    # --- what the barriers imply beyond setter -> waiter
+    # (1) variable-latency instructions of one pipe complete in order, and ptxas puts a barrier only on the LAST MUFU of
+    #     a pair: keep every MUFU (and every LDS) in its original relative order
+    #     (MUFU: at least 8 cycles apart - a warp-wide MUFU occupies the 4-lane XU of the sub-partition for 8 cycles, and
+    #     an instruction that cannot be dispatched blocks the warp's issue)
+    for kind, gap in (("MUFU", 8), ("LDS", 1)):
+        idx = [k for k, x in enumerate(body) if x["op"].startswith(kind)]
+        for a, b in zip(idx, idx[1:]):
+            edges.add((a, b, gap, 0))
+        if len(idx) > 1:
+            edges.add((idx[-1], idx[0], gap, 1))
+    # (2) a consumer of a variable-latency result may carry no wait itself because an EARLIER instruction already waited
+    #     on the covering barrier: every consumer (and every overwriter of the producer's sources) stays behind that wait
+    for pidx, p in enumerate(body):
+        if not is_var(p):
+            continue
+        cover = None  # (barrier index) of p or of the next instruction of the same pipe that sets one
+        for off in range(0, n):
+            q = body[(pidx + off) % n]
+            if q["op"].split(".")[0] == p["op"].split(".")[0] and q["c"]["wr"] != 7:
+                cover = (q["c"]["wr"], (pidx + off))
+                break
+        if cover is None:
+            raise RuntimeError("no covering barrier for " + p["text"])
+        b, qpos = cover
+        w = None
+        for off in range(1, n + 1):
+            k = qpos + off
+            if body[k % n]["c"]["wait"] >> b & 1:
+                w = k
+                break
+        if w is None:
+            raise RuntimeError("nobody waits for barrier %d" % b)
+        wrap_w = w // n - pidx // n  # iterations between p and the wait
+        # consumers / overwriters of p in cyclic order after the wait
+        for off in range(1, n + 1):
+            k = pidx + off
+            c = body[k % n]
+            reads = set().union(*[rs for _, rs in c["s"]]) if c["s"] else set()
+            touches = (reads & p["d"]) or (c["d"] & p["d"]) or (c["d"] & set().union(*[rs for _, rs in p["s"]]))
+            if touches and k > w and (k % n) != (w % n):
+                edges.add((w % n, k % n, 1, k // n - w // n))
+            if c["d"] & p["d"] and k % n != pidx:
+                break  # p's destination is rewritten: later readers belong to the new value
+    # (3) waits on barriers that nothing inside the loop sets guard values produced BEFORE the loop (the target coordinates
+    #     loaded in the prologue): the instruction that carries such a wait stays ahead of everything behind it
+    set_inside = set()
+    for x in body:
+        for b in (x["c"]["wr"], x["c"]["rd"]):
+            if b != 7:
+                set_inside.add(b)
+    for k, x in enumerate(body):
+        if any((x["c"]["wait"] >> b & 1) and b not in set_inside for b in range(6)):
+            for j in range(k + 1, n):
+                edges.add((k, j, 1, 0))
+            for j in range(0, k):
+                edges.add((j, k, 1, 0))   # and what preceded it keeps preceding it
+    return sorted(edges)
+
+
+# ------------------------------------------------------------------------------------------------ cost model / search
+def vec_regs(x):
+    return [(slot, tuple(sorted(r for r in rs if r.startswith("R")))) for slot, rs in x["s"] if any(r.startswith("R") for r in rs)]
+
+
+class Model:
+    def __init__(self, body, edges):
+        self.body, self.n = body, len(body)
+        self.vr = [vec_regs(x) for x in body]
+        self.nreg = [len(set(r for _, rr in v for r in rr)) for v in self.vr]
+        self.f = [is_fma2(x) for x in body]
+        self.m = [x["op"].startswith("MUFU") for x in body]
+        self.ebd = defaultdict(list)
+        self.preds, self.succs = defaultdict(set), defaultdict(set)
+        for (i, j, l, c) in edges:
+            self.ebd[j].append((i, l, c))
+            if c == 0:
+                self.preds[j].add(i)
+                self.succs[i].add(j)
+
+    def cost(self, order):
+        """cycles per loop iteration: issue cost under the register-read model + MUFU neighbour penalties + latency stalls"""
+        n = self.n
+        pos = [0] * n
+        for k, i in enumerate(order):
+            pos[i] = k
+        # registers each FMA-pipe instruction really reads from the register file (operands held in the reuse slots by
+        # the previous FMA-pipe instruction are free; writes invalidate)
+        eff = [None] * n
+        cache = {}
+        for rep in range(2):
+            for k, i in enumerate(order):
+                if self.f[i]:
+                    regs, newcache = set(), {}
+                    for slot, rr in self.vr[i]:
+                        if cache.get(slot) != rr:
+                            regs |= set(rr)
+                        if not (set(rr) & self.body[i]["d"]):
+                            newcache[slot] = rr
+                    eff[k] = regs
+                    cache = newcache
+                else:
+                    d = self.body[i]["d"]
+                    if d:
+                        cache = {s_: rr for s_, rr in cache.items() if not (set(rr) & d)}
+        clock, tprev, tcur = 0.0, {}, {}
+        for rep in range(2):
+            start, tcur = clock, {}
+            for k, i in enumerate(order):
+                e = clock
+                for (p, lat, carried) in self.ebd[i]:
+                    if carried == 0:
+                        if pos[p] >= k:
+                            return 1e9
+                        tp = tcur.get(p)
+                    else:
+                        tp = tprev.get(p)
+                    if tp is not None and tp + lat > e:
+                        e = tp + lat
+                if self.f[i]:
+                    regs = eff[k]
+                    ev = sum(1 for r in regs if int(r[1:]) % 2 == 0)
+                    c = max(2, ev, len(regs) - ev)
+                elif self.m[i]:
+                    c = 0.0
+                    for nk in (k - 1, (k + 1) % n):
+                        if self.f[order[nk]]:
+                            nr = len(eff[nk])
+                            c += 0.375 if nr >= 4 else (0.09 if nr == 3 else 0.0)
+                else:
+                    c = 0.0
+                tcur[i] = e
+                clock = e + c
+            tprev = tcur
+        return clock - start
+
+    def anneal(self, iters, seed, fixed_head=6):
+        random.seed(seed)
+        n = self.n
+        order = list(range(n))
+        cur = best = self.cost(order)
+        best_order = order[:]
+        movable = [i for i in range(n) if self.f[i] or self.m[i]]
+        T = 1.0
+        for it in range(iters):
+            i = random.choice(movable)
+            pos = {x: k for k, x in enumerate(order)}
+            lo = max([pos[p] for p in self.preds[i]], default=-1) + 1
+            hi = min([pos[s] for s in self.succs[i]], default=n) - 1
+            lo, hi, k = max(lo, fixed_head), min(hi, n - 2), pos[i]
+            if lo >= hi:
+                continue
+            newk = random.randint(lo, hi)
+            if newk == k:
+                continue
+            o2 = order[:]
+            o2.pop(k)
+            o2.insert(newk, i)
+            c2 = self.cost(o2)
+            if c2 <= cur or random.random() < math.exp((cur - c2) / T):
+                order, cur = o2, c2
+                if cur < best:
+                    best, best_order = cur, order[:]
+            if it % 10000 == 0:
+                T = max(0.03, T * 0.75)
+                print(f"  anneal {it:7d}: current {cur:7.2f}  best {best:7.2f}", flush=True)
+        return best, best_order
+
+
+# ------------------------------------------------------------------------------------------------ control fields
+def emit(body, order, edges, keep_original_stalls=False):
+    """new (lo, hi) words: stall counts from a nominal issue schedule that honours every edge, reuse flags from adjacency"""
+    n = len(body)
+    seq = [body[i] for i in order]
+    pos = {i: k for k, i in enumerate(order)}
+    ebd = defaultdict(list)
+    for (i, j, l, c) in edges:
+        ebd[j].append((i, l, c))
+    # nominal issue times (ptxas convention: a packed FMA-pipe instruction holds the issue port 2 cycles against the next
+    # FMA-pipe instruction, but an instruction of another pipe may follow after 1)
+    t = [0] * n
+    for k in range(1, n):
+        prev, x = seq[k - 1], seq[k]
+        base = 1
+        if is_fma2(prev) and is_fma2(x):
+            base = 2
+        if not is_fma2(prev) and not prev["op"].startswith("MUFU"):
+            base = max(base, prev["c"]["stall"])        # LDS / uniform / branch keep what ptxas gave them
+        tk = t[k - 1] + base
+        if k >= 2 and is_fma2(seq[k - 2]) and is_fma2(x) and not is_fma2(prev):
+            tk = max(tk, t[k - 2] + 2)                  # FMA2, other, FMA2: the two FMA2 still 2 apart
+        for (p, lat, carried) in ebd[order[k]]:
+            if carried == 0:
+                tk = max(tk, t[pos[p]] + lat)
+        t[k] = tk
+    total = t[n - 1] + seq[n - 1]["c"]["stall"]
+    # carried edges: producer in the previous iteration
+    worst = 0
+    for (i, j, l, c) in edges:
+        if c == 1:
+            worst = max(worst, t[pos[i]] + l - (t[pos[j]] + total))
+    if worst > 0:
+        raise RuntimeError(f"loop-carried latency short by {worst} cycles")
+    out = []
+    for k, x in enumerate(seq):
+        stall = (t[k + 1] - t[k]) if k + 1 < n else x["c"]["stall"]
+        if stall > 15:
+            raise RuntimeError("stall > 15 needed at %d" % k)
+        # operand-reuse flags, the way ptxas uses them in this loop: flag slot s when the next FMA-pipe instruction reads the
+        # same pair in the same slot (an instruction of another pipe in between - a MUFU - does not disturb the operand
+        # collector; barrier waits and a consumer that overwrites the pair are fine) and nothing up to it rewrites the pair
+        reuse = 0
+        if is_fma2(x):
+            nk = k + 1
+            between_writes = set(x["d"])
+            while nk < n and not is_fma2(seq[nk]) and nk - k <= 1:
+                between_writes |= seq[nk]["d"]
+                nk += 1
+            if nk < n and is_fma2(seq[nk]):
+                nxt = dict(vec_regs(seq[nk]))
+                for slot, rr in vec_regs(x):
+                    if len(rr) == 2 and nxt.get(slot) == rr and not (set(rr) & between_writes):
+                        reuse |= 1 << slot
+        out.append((x["lo"], set_ctrl(x["hi"], x["c"]["stall"] if keep_original_stalls else stall, x["c"]["reuse"] if keep_original_stalls else reuse)))
+    return out, total
+
+
+def check_order(order, edges):
+    pos = {i: k for k, i in enumerate(order)}
+    bad = [(i, j) for (i, j, l, c) in edges if c == 0 and pos[i] >= pos[j]]
+    if bad:
+        raise RuntimeError(f"{len(bad)} dependence edges violated, e.g. {bad[:3]}")
+
+
+def hw_search(body, edges, model, base_cubin, offset, kernel_name, a):
+    """Hill climbing with the GPU as the cost function: every candidate order is emitted, patched into the cubin by the
+    evaluation server (tools/kbench --serve) and timed on the device.  Returns (best order, its time, the base time)."""
+    import time
+    n = len(body)
+    kb = os.path.join(REPO, "build", "kbench_r2")
+    cmd = [kb, "--micro", "0", "--n", str(a.hw_n), "--targets", str(a.hw_targets), "--reps", "3", "--check", "0", "--filter", a.hw_filter,
+           "--out", "/dev/null", "--cubin", base_cubin, "--cubin-kernel", kernel_name, "--serve", str(offset)]
+    proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1)
+    while True:
+        line = proc.stdout.readline()
+        if not line:
+            raise RuntimeError("evaluation server died")
+        if line.strip() == "ready":
+            break
+
+    def evaluate(order, verify=False):
+        try:
+            words, _ = emit(body, order, edges)
+        except RuntimeError:
+            return None
+        hexs = b"".join(lo.to_bytes(8, "little") + hi.to_bytes(8, "little") for lo, hi in words).hex()
+        proc.stdin.write(("V " if verify else "T ") + hexs + "\n")
+        proc.stdin.flush()
+        r = proc.stdout.readline().split()
+        if not r or r[0] != "ms":
+            raise RuntimeError("evaluation failed: " + " ".join(r))
+        if verify and int(r[3]) != 0:
+            return -float(r[3])          # NOT bit-identical: a hole in the dependence model (reported, never accepted)
+        return float(r[1])
+
+    order = list(range(n))
+    base = [evaluate(order) for _ in range(8)]
+    t_base = min(base)
+    noise = (sorted(base)[len(base) // 2] - t_base) / t_base
+    print(f"hw: ptxas order {t_base:.4f} ms (8 runs, median-min spread {100 * noise:.3f} %)", flush=True)
+    eps = max(3e-4, 1.5 * noise)
+    random.seed(a.seed)
+    movable = [i for i in range(n) if model.f[i] or model.m[i]]
+    cur, t_cur, t0, evals, accepts = order, t_base, time.time(), 0, 0
+    if a.order_in:
+        import json
+        cur = json.load(open(a.order_in))
+        if isinstance(cur, dict):
+            cur = cur["order"]
+        t_cur = min(evaluate(cur, verify=True) for _ in range(3))
+        print(f"hw: starting from {a.order_in}: {t_cur:.4f} ms ({100 * (t_base / t_cur - 1):+.2f} %)", flush=True)
+        if t_cur < 0:
+            raise RuntimeError("the starting order is not bit-identical")
+    best, t_best = cur, t_cur
+    T = a.hw_temp                       # annealing temperature as a fraction of the run time (0: pure hill climbing)
+    zero_edges = [(i, j) for (i, j, l, c) in edges if c == 0]
+
+    def legal(o):
+        pos = {x: k for k, x in enumerate(o)}
+        return all(pos[i] < pos[j] for (i, j) in zero_edges)
+
+    while time.time() - t0 < a.hw_seconds:
+        # candidate: move one instruction, swap two neighbours, or move a block of 2-3 instructions
+        r = random.random()
+        k = random.randrange(6, n - 2)
+        cand = cur[:]
+        if r < 0.5:
+            L = 1
+        elif r < 0.7:
+            L = 0
+        else:
+            L = random.choice((2, 3))
+        if L == 0:
+            cand[k], cand[k + 1] = cand[k + 1], cand[k]
+            what = f"swap {k}"
+        else:
+            if k + L > n - 1:
+                continue
+            blk = cand[k:k + L]
+            del cand[k:k + L]
+            newk = min(max(6, k + random.randint(-a.hw_window, a.hw_window)), len(cand) - 1)
+            if newk == k:
+                continue
+            cand[newk:newk] = blk
+            what = f"move {L} from {k} to {newk}"
+        if any(not (model.f[i] or model.m[i]) for i in set(cand[max(0, k - 1):k + 4]) ^ set(cur[max(0, k - 1):k + 4])):
+            pass                      # instructions of other pipes may be crossed, they just do not move on their own
+        if not legal(cand):
+            continue
+        t = evaluate(cand)
+        evals += 1
+        if t is None:
+            continue
+        frac = (time.time() - t0) / a.hw_seconds
+        temp = T * (1 - frac)
+        better = t < t_cur * (1 - eps)
+        uphill = (not better) and temp > 0 and t < t_cur * (1 + 4 * temp) and random.random() < math.exp(-(t / t_cur - 1) / temp)
+        if better or uphill:
+            t2 = evaluate(cand, verify=True)   # confirm: a lucky sample must not be accepted, and every accepted
+            evals += 1                         # order is checked bitwise against the original kernel's output
+            if t2 < 0:
+                print(f"hw: REJECTED, not bit-identical ({-t2:.0f} sums differ): {what}", flush=True)
+                continue
+            if (better and t2 < t_cur * (1 - eps / 2)) or (uphill and t2 < t_cur * (1 + 4 * temp)):
+                cur, t_cur = cand, min(t, t2) if better else max(t, t2)
+                accepts += 1
+                if t_cur < t_best:
+                    best, t_best = cur, t_cur
+                    if a.order_out:
+                        import json
+                        json.dump(best, open(a.order_out, "w"))
+                    print(f"hw: {time.time() - t0:6.0f} s  eval {evals:6d}  accept {accepts:4d}  best {t_best:.4f} ms  ({100 * (t_base / t_best - 1):+.2f} %)", flush=True)
+    cur = best
+    finals = [evaluate(cur, verify=True) for _ in range(5)]
+    if min(finals) < 0:
+        raise RuntimeError("the final order is not bit-identical")
+    t_final = min(finals)
+    t_base2 = min(evaluate(order) for _ in range(5))
+    print(f"hw: done, {evals} evaluations, {accepts} accepted; best order {t_final:.4f} ms vs ptxas order {t_base2:.4f} ms: "
+          f"{100 * (t_base2 / t_final - 1):+.2f} %, bit-identical", flush=True)
+    proc.stdin.write("Q\n")
+    proc.stdin.flush()
+    proc.wait()
+    return cur, t_final, t_base2
+
+
+def loop_fingerprint(body):
+    """identifies the exact loop an order was derived from (same source, same ptxas): sha256 over the instruction texts"""
+    import hashlib
+    return hashlib.sha256("\n".join(x["text"] for x in body).encode()).hexdigest()
+
+
+def write_header(path, blob, kernel_name, note):
+    with open(path, "w") as f:
+        f.write("// generated by tools/sass_resched.py - do not edit.  " + note + "\n")
+        f.write(f'static const char force_resched_kernel[] = "{kernel_name}";\n')
+        f.write(f"static const unsigned long long force_resched_cubin_size = {len(blob)}ull;\n")
+        f.write("alignas(16) static const unsigned char force_resched_cubin[] = {\n")
+        if not blob:
+            f.write("0")
+        for k in range(0, len(blob), 32):
+            f.write(",".join(str(b) for b in blob[k:k + 32]) + ",\n")
+        f.write("};\n")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("variant")
+    ap.add_argument("out")
+    ap.add_argument("--iters", type=int, default=300000)
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--identity", action="store_true", help="keep ptxas's order, only regenerate the control fields")
+    ap.add_argument("--copy", action="store_true", help="write the cubin unchanged (loader check)")
+    ap.add_argument("--hw-search", action="store_true", help="search with the GPU as the cost function (needs a B200 and build/kbench_r2)")
+    ap.add_argument("--hw-seconds", type=float, default=300)
+    ap.add_argument("--hw-n", type=int, default=200000)
+    ap.add_argument("--hw-targets", type=int, default=51200)
+    ap.add_argument("--hw-window", type=int, default=10)
+    ap.add_argument("--hw-temp", type=float, default=0.0, help="annealing temperature (relative time), e.g. 0.001")
+    ap.add_argument("--hw-filter", default="t32_r8_tj2_st2")
+    ap.add_argument("--order-in", help="start / use this order (JSON list) instead of ptxas's")
+    ap.add_argument("--order-out", help="write the final order as JSON")
+    ap.add_argument("--emit-header", help="also write the patched cubin as a C array (included by csrc/context.cu); with an order file "
+                                          "whose fingerprint does not match this compiler's loop, an EMPTY array is written and the "
+                                          "library keeps launching the kernel ptxas scheduled")
+    a = ap.parse_args()
+    wd = os.path.dirname(os.path.abspath(a.out))
+    cu, cubin = os.path.join(wd, "resched_src.cu"), os.path.join(wd, "resched_src.cubin")
+    open(cu, "w").write(f'#include "{HDR}"\nnamespace b200nb {{ template __global__ void force_kernel<{a.variant}>(const ForceArgs); }}\n')
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-cubin", "-o", cubin, cu])
+    sass = subprocess.run(["cuobjdump", "-sass", cubin], capture_output=True, text=True).stdout
+    ins = parse_sass(sass)
+    s, e = find_loop(ins)
+    body = ins[s:e + 1]
+    for x in body:
+        x["c"] = ctrl(x["hi"])
+        x["op"], x["d"], x["s"] = operands(x["text"])
+    n = len(body)
+    print(f"hot loop: {n} instructions at 0x{body[0]['addr']:x}-0x{body[-1]['addr']:x}")
+    edges = build_edges(body)
+    model = Model(body, edges)
+    base = model.cost(list(range(n)))
+    print(f"model, ptxas order: {base:.1f} clk per iteration ({base / 16:.2f} per packed pair)")
+    blob0 = open(cubin, "rb").read()
+    orig0 = b"".join(x["lo"].to_bytes(8, "little") + x["hi"].to_bytes(8, "little") for x in body)
+    if a.copy or a.identity:
+        order = list(range(n))
+    elif a.hw_search:
+        kname = re.search(r"Function : (\S+)", sass).group(1)
+        order, t_new, t_old = hw_search(body, edges, model, cubin, blob0.find(orig0), kname, a)
+        print(f"model, hw order   : {model.cost(order):.1f} clk per iteration")
+    elif a.order_in:
+        import json
+        rec = json.load(open(a.order_in))
+        if isinstance(rec, dict):
+            if rec.get("fingerprint") != loop_fingerprint(body):
+                msg = "the order file was derived from a different loop (other compiler version?)"
+                print("sass_resched: " + msg)
+                if a.emit_header:
+                    write_header(a.emit_header, b"", "", "EMPTY: " + msg)
+                    return
+                raise SystemExit(2)
+            order = rec["order"]
+        else:
+            order = rec
+        print(f"model, given order: {model.cost(order):.1f} clk per iteration")
+    else:
+        best, order = model.anneal(a.iters, a.seed)
+        print(f"model, new order  : {best:.1f} clk per iteration ({best / 16:.2f} per packed pair): {100 * (base / best - 1):.1f} % faster")
+    check_order(order, edges)
+    words, total = emit(body, order, edges, keep_original_stalls=a.copy)
+    print(f"nominal issue schedule: {total} cycles per iteration (ptxas: {sum(x['c']['stall'] for x in body)})")
+    blob = bytearray(open(cubin, "rb").read())
+    orig = b"".join(x["lo"].to_bytes(8, "little") + x["hi"].to_bytes(8, "little") for x in body)
+    at = blob.find(orig)
+    if at < 0 or blob.find(orig, at + 1) >= 0:
+        raise RuntimeError("loop bytes not found exactly once in the cubin")
+    new = b"".join(lo.to_bytes(8, "little") + hi.to_bytes(8, "little") for lo, hi in words)
+    if not a.copy:
+        blob[at:at + len(new)] = new
+    open(a.out, "wb").write(blob)
+    if a.order_out:
+        import json
+        json.dump({"variant": a.variant, "fingerprint": loop_fingerprint(body), "instructions": n, "order": order}, open(a.order_out, "w"))
+    if a.emit_header:
+        kname = re.search(r"Function : (\S+)", sass).group(1)
+        write_header(a.emit_header, bytes(blob), kname, f"force_kernel<{a.variant}> with its hot loop re-ordered ({sum(1 for k in range(n) if order[k] != k)} of {n} instructions moved)")
+    changed = sum(1 for k in range(n) if order[k] != k)
+    print(f"wrote {a.out}: {changed} of {n} instructions moved, file offset 0x{at:x}")
+    # the patched loop as text, for the record
+    with open(a.out + ".txt", "w") as f:
+        for k, (lo, hi) in enumerate(words):
+            c = ctrl(hi)
+            f.write(f"{body[0]['addr'] + 16 * k:04x} st={c['stall']:2d} y={c['yld']} wr={c['wr']} rd={c['rd']} wait={c['wait']:06b} ru={c['reuse']:04b} | {body[order[k]]['text']}\n")
+
+
+if __name__ == "__main__":
+    main()
