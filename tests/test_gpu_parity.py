@@ -240,11 +240,14 @@ def test_graph_replay_is_bit_identical(b200, oracle, integrator, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ re-ordered cubin
-@pytest.mark.parametrize("scheme,n,devices", [("galaxy", 200000, [0]), ("random", 50001, [0]), ("galaxy", 120000, [0, 0, 0])])
+@pytest.mark.parametrize("scheme,n,devices", [("galaxy", 200000, [0]), ("random", 50001, [0]), ("galaxy", 120000, [0, 0, 0]),
+                                              ("random", 100000, [0] * 8)])
 def test_reordered_kernel_is_bit_identical(b200, oracle, scheme, n, devices, monkeypatch):
     """The default variant is launched from a cubin whose hot loop was re-ordered after ptxas (tools/sass_resched.py; same
     instructions, registers and arithmetic).  It must agree BIT FOR BIT with the kernel ptxas scheduled
-    (B200NB_NO_RESCHED=1), for the force pass and through a few steps, also on sharded contexts."""
+    (B200NB_NO_RESCHED=1), for the force pass and through a few steps, also on sharded contexts stepped asynchronously
+    (8 shards on one device: short CTAs, kernels of different shards overlapping - the case that exposed a value loaded
+    ahead of the loop being read before its scoreboard wait while the order was being developed)."""
     d = oracle.init_bodies(scheme, n)
     res = {}
     for mode in ("resched", "ptxas"):

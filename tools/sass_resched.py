@@ -87,6 +87,38 @@ def operands(t):
     raise ValueError("unexpected instruction in the hot loop: " + t)
 
 
+def pending_at_entry(ins, start, lookback=400):
+    """[(barrier, resources)] of variable-latency instructions ahead of the loop head (straight-line code, the block-loop
+    header included) whose scoreboard barrier has not been waited for by the time the loop is entered"""
+    out, waited = [], set()
+    for x in reversed(ins[max(0, start - lookback):start]):
+        c = ctrl(x["hi"])
+        for b in range(6):
+            if c["wait"] >> b & 1:
+                waited.add(b)
+        ops = [a.strip() for a in x["text"][len(x["text"].split()[0]):].split(",")]
+        opcode = x["text"].split()[0]
+
+        def regs_of(a, wide=1):
+            m = re.search(r"(?<![A-Za-z])(U?R)(\d+)", a.replace(".reuse", ""))
+            if not m:
+                m2 = re.search(r"(U?P\d)", a)
+                return {m2.group(1)} if m2 else set()
+            return {f"{m.group(1)}{int(m.group(2)) + k}" for k in range(wide)}
+
+        wide = 4 if ".128" in opcode else (2 if ".64" in opcode else 1)
+        if c["wr"] != 7 and c["wr"] not in waited and ops and ops[0]:
+            out.append((c["wr"], regs_of(ops[0], wide)))
+        if c["rd"] != 7 and c["rd"] not in waited:
+            res = set()
+            for a in ops[1:]:
+                res |= regs_of(a)
+            out.append((c["rd"], res))
+        if x["text"].startswith(("EXIT", "RET")):
+            break
+    return [(b, r) for b, r in out if r]
+
+
 def find_loop(ins):
     """the backward-branch region with the most FFMA2"""
     by_addr = {x["addr"]: k for k, x in enumerate(ins)}
@@ -207,8 +239,11 @@ def build_edges(body):
                 edges.add((w % n, k % n, 1, k // n - w // n))
             if c["d"] & p["d"] and k % n != pidx:
                 break  # p's destination is rewritten: later readers belong to the new value
-    # (3) waits on barriers that nothing inside the loop sets guard values produced BEFORE the loop (the target coordinates
-    #     loaded in the prologue): the instruction that carries such a wait stays ahead of everything behind it
+    # (3) values produced BEFORE the loop by variable-latency instructions (the target coordinates loaded in the prologue,
+    #     LDCU of soft^2 in the block-loop header) are guarded by the FIRST in-loop wait on their barrier - also when that
+    #     barrier index is used again inside the loop.  `entry` = [(barrier, resources)] from the code ahead of the loop:
+    #     every in-loop instruction that touches such a resource stays behind the first waiter; a wait on a barrier that
+    #     nothing inside the loop sets pins its instruction in place altogether.
     set_inside = set()
     for x in body:
         for b in (x["c"]["wr"], x["c"]["rd"]):
@@ -220,6 +255,18 @@ def build_edges(body):
                 edges.add((k, j, 1, 0))
             for j in range(0, k):
                 edges.add((j, k, 1, 0))   # and what preceded it keeps preceding it
+    for b, res in (body[0].get("entry") or []):
+        w = next((k for k, x in enumerate(body) if x["c"]["wait"] >> b & 1), None)
+        if w is None:
+            raise RuntimeError(f"barrier {b} is pending at loop entry and nothing in the loop waits for it")
+        for j, x in enumerate(body):
+            if j == w:
+                continue
+            reads = set().union(*[rs for _, rs in x["s"]]) if x["s"] else set()
+            if (reads | x["d"]) & res:
+                if j < w:
+                    raise RuntimeError(f"instruction {j} touches {res} ahead of the wait on barrier {b}")
+                edges.add((w, j, 2, 0))
     return sorted(edges)
 
 
@@ -572,6 +619,8 @@ def main():
         x["op"], x["d"], x["s"] = operands(x["text"])
     n = len(body)
     print(f"hot loop: {n} instructions at 0x{body[0]['addr']:x}-0x{body[-1]['addr']:x}")
+    body[0]["entry"] = pending_at_entry(ins, s)
+    print("pending at loop entry (barrier, resources): " + ", ".join(f"SB{b}:{sorted(r)}" for b, r in body[0]["entry"]))
     edges = build_edges(body)
     model = Model(body, edges)
     base = model.cost(list(range(n)))
