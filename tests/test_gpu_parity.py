@@ -220,13 +220,15 @@ def test_energy_matches_oracle_and_leapfrog_conserves(b200, oracle):
     assert drift[1] < 1e-3 and drift[1] <= drift[0], drift
 
 
+@pytest.mark.parametrize("n", [3000, 60000])
 @pytest.mark.parametrize("integrator", [0, 1])
-def test_graph_replay_is_bit_identical(b200, oracle, integrator, monkeypatch):
+def test_graph_replay_is_bit_identical(b200, oracle, integrator, n, monkeypatch):
     """b200nb_step(n_steps >= 32) replays a captured CUDA graph of 16 iterations; it must be the same arithmetic as
-    stepping one iteration at a time."""
-    n = 3000
+    stepping one iteration at a time.  n = 3000 runs the small R = 2 kernel, n = 60000 the default kernel, which is
+    launched through the driver API from the re-ordered cubin (cuLaunchKernel inside the stream capture)."""
     d = oracle.init_bodies("random", n)
     with make_ctx(b200, d) as ctx:
+        assert ("_r8_" in ctx.kernel_name) == (n == 60000), ctx.kernel_name
         for _ in range(70):
             ctx.step(DT, integrator, 1)
         ref = ctx.download_state()
