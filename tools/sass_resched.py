@@ -482,7 +482,6 @@ def hw_search(body, edges, model, base_cubin, offset, kernel_name, a):
     print(f"hw: ptxas order {t_base:.4f} ms (8 runs, median-min spread {100 * noise:.3f} %)", flush=True)
     eps = max(3e-4, 1.5 * noise)
     random.seed(a.seed)
-    movable = [i for i in range(n) if model.f[i] or model.m[i]]
     cur, t_cur, t0, evals, accepts = order, t_base, time.time(), 0, 0
     if a.order_in:
         import json
@@ -525,8 +524,6 @@ def hw_search(body, edges, model, base_cubin, offset, kernel_name, a):
                 continue
             cand[newk:newk] = blk
             what = f"move {L} from {k} to {newk}"
-        if any(not (model.f[i] or model.m[i]) for i in set(cand[max(0, k - 1):k + 4]) ^ set(cur[max(0, k - 1):k + 4])):
-            pass                      # instructions of other pipes may be crossed, they just do not move on their own
         if not legal(cand):
             continue
         t = evaluate(cand)
