@@ -70,3 +70,8 @@ def test_b200_arm_line():
     assert r["kernel_share_of_step"] > 0.99
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert "workload" in d["config"] and "200000" in d["config"]["workload"]
+    # both arms describe the workload with the identical `config` object (the driver compares them)
+    if os.path.exists(os.path.join(REPO, "oracle", "_ref", "libmurbref.so")):
+        ref = _run(["--impl", "reference", "--steps", "5", "--warmup", "3"], 900)
+        assert ref["config"] == d["config"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
+        assert ref["cpu_baseline"]["same_config"] is True
